@@ -1,0 +1,98 @@
+"""Generates the golden fixtures under tests/golden/ by running the UNMODIFIED reference
+(/root/reference, imported through tests/golden/ref_loader.py) on seeded synthetic inputs.
+
+Run in the build container only:   python tests/golden/make_golden.py
+The GPU box has no /root/reference; the committed .npz files are what travels.
+
+Every fixture stores the inputs (so nothing depends on re-generating them bit-identically on another
+host), the hyper-parameters, and the reference outputs: the two losses, autograd gradients of
+(loss_photometric + loss_smoothness) w.r.t. every inverse-depth map and the pose vectors, the
+per-scale argmin selection, and -- for the first case -- scale-0 intermediates (coordinates, warped
+image, per-pixel photometric maps) obtained by calling the reference's own methods.
+"""
+from __future__ import annotations
+
+import os
+import sys
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, HERE)
+sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+
+import ref_loader  # noqa: E402
+from mgnet_b200.synthetic import make_inputs, snap_pose_trig  # noqa: E402
+
+CASES = {
+    # name: (make_inputs kwargs, hyper-parameter overrides, keep scale-0 intermediates)
+    "kitti_small_mask": (dict(B=2, H=48, W=64, n=3, seed=1, noise=0.2), {}, True),
+    "grad_smooth_shift": (dict(B=2, H=48, W=64, n=3, seed=2, noise=0.0, shift_sources=True), {}, False),
+    "nomask_n1": (dict(B=1, H=32, W=96, n=1, seed=3, noise=0.2, with_mask=False), {}, False),
+    "ragged_n4_bigpose": (dict(B=2, H=40, W=72, n=4, seed=4, noise=0.1, pose_scale=0.05), {}, False),
+    "automask_off": (dict(B=1, H=32, W=64, n=2, seed=5, noise=0.2), {"automask_loss": False}, False),
+    "weights_alpha": (dict(B=1, H=36, W=68, n=2, seed=6, noise=0.0, shift_sources=True),
+                      {"ssim_loss_weight": 0.5, "photometric_loss_weight": 2.0, "smoothing_loss_weight": 0.05}, False),
+}
+
+
+def adversarial(pred, tgt):
+    """ragged_n4_bigpose: points behind the camera, fully out-of-bounds warps, clamped inverse depth,
+    an all-false mask row block."""
+    poses = pred["poses"].clone()
+    poses[0, 0] = torch.tensor([0.3, -0.1, -4.0, 0.02, 0.4, -0.03])   # tz=-4: most points behind the camera
+    poses[1, 1] = torch.tensor([30.0, 2.0, 0.5, 0.0, 0.0, 0.7])       # far out of bounds
+    pred["poses"] = snap_pose_trig(poses)
+    pred["depth"][1][0, 0, :5, :7] = 0.0          # clamp(min=1e-6) active
+    pred["depth"][2][1, 0, 10:12, :] = 1e-7
+    tgt["reprojection_mask"][0, 0, 20:30, :] = False
+    tgt["reprojection_mask"][1, 0, :, 60:] = False
+    return pred, tgt
+
+
+def main():
+    for name, (kw, hp_over, keep) in CASES.items():
+        pred, tgt = make_inputs(**kw)
+        if name == "ragged_n4_bigpose":
+            pred, tgt = adversarial(pred, tgt)
+        hp = dict(ref_loader.DEFAULT_HP)
+        hp.update(hp_over)
+        res = ref_loader.run_reference(pred, tgt, hp=hp, want_grads=True, want_intermediates=True)
+        n = len(pred["depth"])
+        out = {
+            "in_image_orig": tgt["image_orig"].numpy(),
+            "in_image_prev_orig": tgt["image_prev_orig"].numpy(),
+            "in_image_next_orig": tgt["image_next_orig"].numpy(),
+            "in_camera_matrix": tgt["camera_matrix"].numpy(),
+            "in_poses": pred["poses"].numpy(),
+            "hp_ssim_loss_weight": np.float64(hp["ssim_loss_weight"]),
+            "hp_photometric_loss_weight": np.float64(hp["photometric_loss_weight"]),
+            "hp_smoothing_loss_weight": np.float64(hp["smoothing_loss_weight"]),
+            "hp_automask_loss": np.bool_(hp["automask_loss"]),
+            "loss_photometric": res["loss_photometric"],
+            "loss_smoothness": res["loss_smoothness"],
+            "grad_poses": res["grad_poses"],
+            "pose_mat": np.stack([res["pose_mat_0"], res["pose_mat_1"]], 1),
+        }
+        if "reprojection_mask" in tgt:
+            out["in_reprojection_mask"] = tgt["reprojection_mask"].numpy()
+        for i in range(n):
+            out["in_depth_%d" % i] = pred["depth"][i].numpy()
+            out["grad_depth_%d" % i] = res["grad_depth_%d" % i]
+            out["sel_%d" % i] = res["sel_%d" % i]
+        if keep:
+            for s in range(2):
+                for k in ("coords", "warped", "photo"):
+                    out["%s_0_%d" % (k, s)] = res["%s_0_%d" % (k, s)]
+                out["identity_%d" % s] = res["identity_%d" % s]
+            out["minmap_0"] = res["minmap_0"]
+        path = os.path.join(HERE, name + ".npz")
+        np.savez_compressed(path, **out)
+        print("%-20s %7.1f KB  Lp=%.8f Ls=%.8e" % (name, os.path.getsize(path) / 1024.0,
+                                                  float(res["loss_photometric"]), float(res["loss_smoothness"])))
+
+
+if __name__ == "__main__":
+    torch.set_num_threads(1)   # the reference on CPU is thread-count independent; be safe
+    main()
