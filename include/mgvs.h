@@ -1,0 +1,124 @@
+/*
+ * mgvs.h -- C ABI of the B200-native view-synthesis loss (libmgvs.so, built for sm_100a).
+ *
+ * The reference (uulm-mrm/MGNet) has no FFI for this path: the loss is a Python nn.Module that is
+ * constructor-injected into the depth head (mgnet/modeling/mg_net.py:744,757,772-779) and called as
+ * self.loss(predictions, targets) (mg_net.py:827-829).  The entry points below are what a binding
+ * for that call binds; each cites the reference code it replaces.  INTEGRATION.md shows the
+ * ctypes stub a maintainer adds on the reference side.
+ *
+ * Conventions: plain pointers and sizes only (no torch types); every pointer is DEVICE memory unless
+ * the name ends in _host; all tensors are contiguous NCHW fp32 as guaranteed by
+ * custom_fwd(cast_inputs=torch.float32) (mg_net.py:827); the library never allocates or frees device
+ * memory, never synchronises the device and launches only on the stream it is given; every call is
+ * CUDA-graph capturable.  Return value: 0 on success, a negative MGVS_E* code otherwise, with a
+ * thread-local message retrievable through mgvs_last_error().
+ */
+#ifndef MGVS_H_
+#define MGVS_H_
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MGVS_ABI_VERSION 1
+#define MGVS_MAX_SCALES 8   /* n: number of inverse-depth maps (reference: 3, mg_net.py:760-764) */
+#define MGVS_NUM_SOURCES 2  /* S: prev, next -- hard-coded in the reference (loss.py:116) */
+
+enum {
+    MGVS_OK = 0,
+    MGVS_EINVAL = -1,       /* bad dims / null pointer / misaligned pointer */
+    MGVS_EUNSUPPORTED = -2, /* legal in the reference but not implemented (padding_mode != zeros, ...) */
+    MGVS_EWORKSPACE = -3,   /* workspace too small */
+    MGVS_ECUDA = -4         /* launch failure */
+};
+
+/* One problem instance == one call of MultiViewPhotometricLoss.forward (loss.py:111-154). */
+typedef struct MgvsProblem {
+    int B, H, W, n;
+    const float *target;                      /* targets["image_orig"]       [B,3,H,W]  (loss.py:125) */
+    const float *source[MGVS_NUM_SOURCES];    /* image_prev_orig, image_next_orig       (loss.py:116) */
+    const float *inv_depth[MGVS_MAX_SCALES];  /* predictions["depth"][i]     [B,1,H,W]  (loss.py:112) */
+    const float *camera;                      /* targets["camera_matrix"]; element (b,r,c) at
+                                                 camera[b*cam_batch_stride + r*cam_row_stride + c];
+                                                 only [:, :3, :3] is read       (loss.py:122-123) */
+    long long cam_batch_stride, cam_row_stride;
+    const float *poses;                       /* predictions["poses"]        [B,S,6] (tx,ty,tz,rx,ry,rz)
+                                                 target->source, Euler        (loss.py:117-119) */
+    const unsigned char *mask;                /* targets["reprojection_mask"] [B,1,H,W] bool, or NULL
+                                                 (loss.py:147, 237-238) */
+    /* MultiViewPhotometricLoss.__init__ arguments (loss.py:87-109, defaults config.py:108-117) */
+    float ssim_weight;          /* float32(ssim_loss_weight) */
+    float one_minus_ssim_weight;/* float32(1 - ssim_loss_weight) evaluated in double like Python does */
+    float photometric_weight;
+    float smoothing_weight;
+    int automask;               /* automask_loss */
+    int reduce_op;              /* 0 = "min" (the only one implemented) */
+    int padding_mode;           /* 0 = "zeros" (the only one implemented) */
+    void *workspace;            /* >= mgvs_workspace_bytes(B,H,W,n) bytes, 256-byte aligned; must stay
+                                   untouched between mgvs_forward and the matching mgvs_backward */
+    size_t workspace_bytes;
+} MgvsProblem;
+
+int mgvs_abi_version(void);
+const char *mgvs_last_error(void);
+
+/* Scratch the caller must provide (per-tile partial sums, camera table, pose-gradient partials). */
+size_t mgvs_workspace_bytes(int B, int H, int W, int n);
+
+/* Number of doubles in the partial-sum vector: 3n+3 =
+ *   [0,n)     sum over masked pixels of the per-pixel minimum photometric loss, per scale (loss.py:245)
+ *   [n]       N   = number of true mask entries                                      (loss.py:245)
+ *   [n+1,2n+1)  sum of mask*|d/dx d_hat|*w_x per scale, already divided by the per-image mean (depth.py:48-51)
+ *   [2n+1,3n+1) same in y
+ *   [3n+1]    N_x, [3n+2] N_y                                                        (loss.py:285-286)
+ * These are the only values that cross GPUs: the caller all-reduces (sum) this vector between
+ * mgvs_forward and mgvs_finalize when the batch is sharded. */
+int mgvs_num_sums(int n);
+
+/* Fused forward: K^-1 back-projection, SE(3), projection, bilinear sampling of both sources, SSIM+L1,
+ * identity automask, per-pixel min, smoothness.  Replaces loss.py:111-149 + geometry/*.
+ *   sel  [n,B,H,W] uint8 out (may be NULL): argmin index in the reference's list order
+ *        [warp_prev, id_prev, warp_next, id_next] (automask) or [warp_prev, warp_next]; ties -> lowest.
+ *   sums [3n+3] double out: this rank's partial sums (see above). */
+int mgvs_forward(const MgvsProblem *p, unsigned char *sel, double *sums, void *cuda_stream);
+
+/* Turns (globally reduced) sums into the two weighted scalars of loss.py:151-154.
+ *   losses [2] float out: loss_photometric, loss_smoothness. */
+int mgvs_finalize(const MgvsProblem *p, const double *sums, float *losses, void *cuda_stream);
+
+/* Fused backward (recomputes the forward from the same tiles).  Replaces the autograd replay of the
+ * loss graph.
+ *   sel, sums   as produced by mgvs_forward (sums after the all-reduce if sharded)
+ *   g_losses    [2] float, upstream gradients of (loss_photometric, loss_smoothness)
+ *   grad_inv[i] [B,1,H,W] float out, fully overwritten
+ *   grad_poses  [B,S,6] float out, fully overwritten; deterministic (no float atomics) */
+int mgvs_backward(const MgvsProblem *p, const unsigned char *sel, const double *sums, const float *g_losses,
+                  float *const *grad_inv, float *grad_poses, void *cuda_stream);
+
+/* ---- mgnet.geometry primitives (forward only) ---------------------------------------------------- */
+
+/* view_synthesis (camera_utils.py:24-54): warped[B,3,H,W] = grid_sample(ref_image, project(reconstruct(depth))).
+ * depth is METRIC depth (already 1/inv); pose34 is [B,3,4] (R|t) of ref_cam.Tcw, K as in MgvsProblem. */
+int mgvs_view_synthesis(int B, int H, int W, const float *ref_image, const float *depth, const float *camera,
+                        long long cam_batch_stride, long long cam_row_stride, const float *pose34,
+                        float *warped, float *coords /* [B,H,W,2] or NULL */, void *cuda_stream);
+
+/* Camera.reconstruct(depth, frame="c") (camera.py:107-136): points[B,3,H,W] = (K^-1 grid) * depth. */
+int mgvs_reconstruct(int B, int H, int W, const float *depth, const float *camera, long long cam_batch_stride,
+                     long long cam_row_stride, float *points, void *cuda_stream);
+
+/* Camera.project(X, frame) (camera.py:143-182): coords[B,H,W,2] normalised to [-1,1] (align_corners=True);
+ * pose34 [B,3,4] = Tcw for frame "w", NULL for frame "c". */
+int mgvs_project(int B, int H, int W, const float *points, const float *camera, long long cam_batch_stride,
+                 long long cam_row_stride, const float *pose34, float *coords, void *cuda_stream);
+
+/* Self-test hook used by the GPU tests: out[i] = a[i] / b[i] with the library's in-kernel exact division. */
+int mgvs_test_div(const float *a, const float *b, float *out, long long count, void *cuda_stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MGVS_H_ */

@@ -1,0 +1,453 @@
+// mgvs_api.cu -- small kernels (camera table, fixed-order reductions, finalise, pose chain) and the
+// extern "C" entry points declared in include/mgvs.h.  Built for sm_100a only.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "../../include/mgvs.h"
+#include "mgvs_bwd.cuh"
+#include "mgvs_fwd.cuh"
+
+namespace mgvs {
+
+static thread_local char g_err[256] = "";
+static int fail(int code, const char* msg)
+{
+    snprintf(g_err, sizeof(g_err), "%s", msg);
+    return code;
+}
+
+// ---------------------------------------------------------------------------------------------
+// workspace layout (all offsets 256-byte aligned)
+struct Layout {
+    size_t cams, partials, imgsums, counter, pose_partials, total;
+    int tiles_x, tiles_y, tiles;
+};
+static inline size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
+static Layout make_layout(int B, int H, int W, int n)
+{
+    Layout L;
+    L.tiles_x = (W + TW - 1) / TW;
+    L.tiles_y = (H + TH - 1) / TH;
+    L.tiles = B * L.tiles_x * L.tiles_y;
+    size_t off = 0;
+    L.cams = off; off = align256(off + sizeof(Cam) * (size_t)B);
+    L.partials = off; off = align256(off + sizeof(double) * (size_t)L.tiles * (4 * n + 3));
+    L.imgsums = off; off = align256(off + sizeof(double) * (size_t)B * (4 * n + 3));
+    L.counter = off; off = align256(off + 256);
+    L.pose_partials = off; off = align256(off + sizeof(float) * (size_t)L.tiles * 24);
+    L.total = off;
+    return L;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Camera table: K, Kinv (camera.py:72-81) and R|t per source (pose_utils.py:9-51, pose.py:41-47).
+// sin/cos are the correctly rounded fp32 values (fp64 evaluation); the two tiny bmm's of euler2mat
+// round like ATen's small-matrix path: acc = 0; acc += a*b with separately rounded mul and add.
+__global__ void prep_kernel(int B, const float* __restrict__ camera, long long cbs, long long crs,
+                            const float* __restrict__ poses, Cam* __restrict__ cams)
+{
+    int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    Cam c;
+    for (int r = 0; r < 3; r++)
+        for (int k = 0; k < 3; k++) c.K[r * 3 + k] = camera[b * cbs + r * crs + k];
+    for (int k = 0; k < 9; k++) c.Kinv[k] = c.K[k];
+    float fx = c.K[0], fy = c.K[4], cx = c.K[2], cy = c.K[5];
+    c.Kinv[0] = __fdiv_rn(1.0f, fx);
+    c.Kinv[4] = __fdiv_rn(1.0f, fy);
+    c.Kinv[2] = __fdiv_rn(__fmul_rn(-1.0f, cx), fx);
+    c.Kinv[5] = __fdiv_rn(__fmul_rn(-1.0f, cy), fy);
+    for (int s = 0; s < S; s++) {
+        const float* v = poses + ((size_t)b * S + s) * 6;
+        float cxr = (float)cos((double)v[3]), sxr = (float)sin((double)v[3]);
+        float cyr = (float)cos((double)v[4]), syr = (float)sin((double)v[4]);
+        float czr = (float)cos((double)v[5]), szr = (float)sin((double)v[5]);
+        float z0 = __fmul_rn(v[5], 0.0f), o1 = __fadd_rn(z0, 1.0f);
+        float zm[9] = {czr, -szr, z0, szr, czr, z0, z0, z0, o1};
+        float ym[9] = {cyr, z0, syr, z0, o1, z0, -syr, z0, cyr};
+        float xm[9] = {o1, z0, z0, z0, cxr, -sxr, z0, sxr, cxr};
+        float xy[9], R[9];
+        for (int pass = 0; pass < 2; pass++) {
+            const float* A = pass ? xy : xm;
+            const float* Bm = pass ? zm : ym;
+            float* C = pass ? R : xy;
+            for (int r = 0; r < 3; r++)
+                for (int k = 0; k < 3; k++) {
+                    float acc = 0.0f;
+                    for (int j = 0; j < 3; j++) acc = __fadd_rn(acc, __fmul_rn(A[r * 3 + j], Bm[j * 3 + k]));
+                    C[r * 3 + k] = acc;
+                }
+        }
+        for (int r = 0; r < 3; r++) {
+            c.Rt[s][r * 4 + 0] = R[r * 3 + 0];
+            c.Rt[s][r * 4 + 1] = R[r * 3 + 1];
+            c.Rt[s][r * 4 + 2] = R[r * 3 + 2];
+            c.Rt[s][r * 4 + 3] = v[r];
+        }
+    }
+    for (int k = 0; k < 6; k++) c.pad[k] = 0.f;
+    cams[b] = c;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Fixed-order reduction of the per-tile partial sums: one CTA per image, then the last CTA to finish
+// folds the per-image sums (smoothness normalised by the per-image mean, depth.py:48-51) into the
+// rank-level vector [3n+3].
+__global__ void __launch_bounds__(256) reduce_kernel(int B, int n, int tiles_per_image, long long HW,
+                                                     const double* __restrict__ partials, double* __restrict__ imgsums,
+                                                     unsigned int* __restrict__ counter, double* __restrict__ sums)
+{
+    __shared__ double sh[256];
+    __shared__ bool last;
+    const int b = blockIdx.x, nq = 4 * n + 3, tid = threadIdx.x;
+    for (int q = 0; q < nq; q++) {
+        double acc = 0.0;
+        for (int t = tid; t < tiles_per_image; t += 256) acc += partials[((size_t)b * tiles_per_image + t) * nq + q];
+        sh[tid] = acc;
+        __syncthreads();
+        for (int o = 128; o > 0; o >>= 1) {
+            if (tid < o) sh[tid] += sh[tid + o];
+            __syncthreads();
+        }
+        if (tid == 0) imgsums[(size_t)b * nq + q] = sh[0];
+        __syncthreads();
+    }
+    if (tid == 0) {
+        __threadfence();
+        unsigned int done = atomicAdd(counter, 1u);
+        last = (done == (unsigned)B - 1);
+    }
+    __syncthreads();
+    if (!last) return;
+    __threadfence();
+    if (tid < 3 * n + 3) {
+        double acc = 0.0;
+        for (int bb = 0; bb < B; bb++) {
+            const volatile double* is = imgsums + (size_t)bb * nq;
+            if (tid < n) acc += is[tid];                                    // photometric sums
+            else if (tid == n) acc += is[4 * n];                            // N
+            else if (tid < 3 * n + 1) {                                     // smoothness x / y
+                int which = (tid - n - 1) / n, i = (tid - n - 1) % n;
+                double mean = is[3 * n + i] / (double)HW;
+                double c = mean < 1e-6 ? 1e-6 : mean;
+                acc += is[(1 + which) * n + i] / c;
+            } else acc += is[4 * n + 1 + (tid - 3 * n - 1)];                // Nx, Ny
+        }
+        sums[tid] = acc;
+    }
+}
+
+// loss.py:151-154, 252-254, 274-294
+__global__ void finalize_kernel(int n, const double* __restrict__ sums, float photo_w, float smooth_w,
+                                float* __restrict__ losses)
+{
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    double N = sums[n], Nx = sums[3 * n + 1], Ny = sums[3 * n + 2];
+    double lp = 0.0, ls = 0.0;
+    for (int i = 0; i < n; i++) {
+        lp += sums[i] / N;
+        ls += (sums[n + 1 + i] / Nx + sums[2 * n + 1 + i] / Ny) / (double)(1 << i);
+    }
+    losses[0] = (float)(lp / (double)n * (double)photo_w);
+    losses[1] = (float)(ls / (double)n * (double)smooth_w);
+}
+
+// Pose gradient: fixed-order sum of the per-tile partials of dL/d(R|t), then the Euler chain through
+// R = Rx Ry Rz (pose_utils.py:14-38); vec = (tx,ty,tz,rx,ry,rz).  One CTA per (image, source).
+__global__ void __launch_bounds__(128) pose_reduce_kernel(int tiles_per_image, const float* __restrict__ pose_partials,
+                                                          const float* __restrict__ poses, float* __restrict__ grad_poses)
+{
+    __shared__ double sh[12][128];
+    __shared__ double g[12];
+    const int bs = blockIdx.x, b = bs / S, s = bs % S, tid = threadIdx.x;
+    double acc[12];
+    for (int j = 0; j < 12; j++) acc[j] = 0.0;
+    for (int t = tid; t < tiles_per_image; t += 128) {
+        const float* pp = pose_partials + ((size_t)b * tiles_per_image + t) * 24 + s * 12;
+        for (int j = 0; j < 12; j++) acc[j] += (double)pp[j];
+    }
+    for (int j = 0; j < 12; j++) sh[j][tid] = acc[j];
+    __syncthreads();
+    for (int o = 64; o > 0; o >>= 1) {
+        if (tid < o)
+            for (int j = 0; j < 12; j++) sh[j][tid] += sh[j][tid + o];
+        __syncthreads();
+    }
+    if (tid < 12) g[tid] = sh[tid][0];
+    __syncthreads();
+    if (tid != 0) return;
+    const float* v = poses + (size_t)bs * 6;
+    double cx = cos((double)v[3]), sx = sin((double)v[3]);
+    double cy = cos((double)v[4]), sy = sin((double)v[4]);
+    double cz = cos((double)v[5]), sz = sin((double)v[5]);
+    double Rx[9] = {1, 0, 0, 0, cx, -sx, 0, sx, cx}, dRx[9] = {0, 0, 0, 0, -sx, -cx, 0, cx, -sx};
+    double Ry[9] = {cy, 0, sy, 0, 1, 0, -sy, 0, cy}, dRy[9] = {-sy, 0, cy, 0, 0, 0, -cy, 0, -sy};
+    double Rz[9] = {cz, -sz, 0, sz, cz, 0, 0, 0, 1}, dRz[9] = {-sz, -cz, 0, cz, -sz, 0, 0, 0, 0};
+    float* gp = grad_poses + (size_t)bs * 6;
+    for (int a = 0; a < 3; a++) {
+        const double* M0 = a == 0 ? dRx : Rx;
+        const double* M1 = a == 1 ? dRy : Ry;
+        const double* M2 = a == 2 ? dRz : Rz;
+        double T[9], D[9];
+        for (int r = 0; r < 3; r++)
+            for (int c = 0; c < 3; c++) {
+                double t = 0;
+                for (int k = 0; k < 3; k++) t += M0[r * 3 + k] * M1[k * 3 + c];
+                T[r * 3 + c] = t;
+            }
+        for (int r = 0; r < 3; r++)
+            for (int c = 0; c < 3; c++) {
+                double t = 0;
+                for (int k = 0; k < 3; k++) t += T[r * 3 + k] * M2[k * 3 + c];
+                D[r * 3 + c] = t;
+            }
+        double ga = 0;
+        for (int r = 0; r < 3; r++)
+            for (int c = 0; c < 3; c++) ga += g[r * 4 + c] * D[r * 3 + c];
+        gp[3 + a] = (float)ga;
+    }
+    for (int r = 0; r < 3; r++) gp[r] = (float)g[r * 4 + 3];
+}
+
+__global__ void test_div_kernel(const float* a, const float* b, float* out, long long count)
+{
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < count) out[i] = exact::div(a[i], b[i]);
+}
+
+// ---- standalone geometry primitives ------------------------------------------------------------
+__global__ void view_synthesis_kernel(int B, int H, int W, const float* __restrict__ ref, const float* __restrict__ depth,
+                                      const float* __restrict__ camera, long long cbs, long long crs,
+                                      const float* __restrict__ pose34, float* __restrict__ warped, float* __restrict__ coords)
+{
+    const int HW = H * W;
+    long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (long long)B * HW) return;
+    int b = (int)(idx / HW), pix = (int)(idx - (long long)b * HW), v = pix / W, u = pix - v * W;
+    float K[9], Kinv[9], Rt[12];
+    for (int r = 0; r < 3; r++)
+        for (int k = 0; k < 3; k++) K[r * 3 + k] = camera[b * cbs + r * crs + k];
+    for (int k = 0; k < 9; k++) Kinv[k] = K[k];
+    Kinv[0] = __fdiv_rn(1.0f, K[0]);
+    Kinv[4] = __fdiv_rn(1.0f, K[4]);
+    Kinv[2] = __fdiv_rn(__fmul_rn(-1.0f, K[2]), K[0]);
+    Kinv[5] = __fdiv_rn(__fmul_rn(-1.0f, K[5]), K[4]);
+    for (int k = 0; k < 12; k++) Rt[k] = pose34[(size_t)b * 12 + k];
+    float r[3], Xc[3];
+    exact::ray(Kinv, u, v, r);
+    float d = depth[idx];
+    for (int j = 0; j < 3; j++) Xc[j] = __fmul_rn(r[j], d);
+    const float wm1 = (float)(W - 1), hm1 = (float)(H - 1);
+    exact::Proj pr;
+    exact::project(K, Rt, Xc, wm1, hm1, exact::rcp_refined(wm1), exact::rcp_refined(hm1), pr);
+    exact::Cell c;
+    exact::cell(pr.ix, pr.iy, H, W, c);
+    float wnw = __fmul_rn(c.wN, c.wW), wne = __fmul_rn(c.wN, c.wE), wsw = __fmul_rn(c.wS, c.wW), wse = __fmul_rn(c.wS, c.wE);
+    for (int ch = 0; ch < 3; ch++) {
+        float vals[4];
+        warped[((size_t)b * 3 + ch) * HW + pix] = exact::blend(ref + ((size_t)b * 3 + ch) * HW, W, c, wnw, wne, wsw, wse, vals);
+    }
+    if (coords) {
+        float xn = __fadd_rn(exact::div(__fadd_rn(pr.ax, pr.ax), wm1), -1.0f);
+        float yn = __fadd_rn(exact::div(__fadd_rn(pr.ay, pr.ay), hm1), -1.0f);
+        coords[idx * 2] = xn;
+        coords[idx * 2 + 1] = yn;
+    }
+}
+
+__global__ void reconstruct_kernel(int B, int H, int W, const float* __restrict__ depth, const float* __restrict__ camera,
+                                   long long cbs, long long crs, float* __restrict__ points)
+{
+    const int HW = H * W;
+    long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (long long)B * HW) return;
+    int b = (int)(idx / HW), pix = (int)(idx - (long long)b * HW), v = pix / W, u = pix - v * W;
+    float K[9], Kinv[9];
+    for (int r = 0; r < 3; r++)
+        for (int k = 0; k < 3; k++) K[r * 3 + k] = camera[b * cbs + r * crs + k];
+    for (int k = 0; k < 9; k++) Kinv[k] = K[k];
+    Kinv[0] = __fdiv_rn(1.0f, K[0]);
+    Kinv[4] = __fdiv_rn(1.0f, K[4]);
+    Kinv[2] = __fdiv_rn(__fmul_rn(-1.0f, K[2]), K[0]);
+    Kinv[5] = __fdiv_rn(__fmul_rn(-1.0f, K[5]), K[4]);
+    float r[3];
+    exact::ray(Kinv, u, v, r);
+    float d = depth[idx];
+    for (int j = 0; j < 3; j++) points[((size_t)b * 3 + j) * HW + pix] = __fmul_rn(r[j], d);
+}
+
+// Camera.project (camera.py:143-182): X[B,3,H,W] -> normalised coords [B,H,W,2]; pose34 == nullptr is frame "c".
+__global__ void project_kernel(int B, int H, int W, const float* __restrict__ X, const float* __restrict__ camera,
+                               long long cbs, long long crs, const float* __restrict__ pose34, float* __restrict__ coords)
+{
+    const int HW = H * W;
+    long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (long long)B * HW) return;
+    int b = (int)(idx / HW), pix = (int)(idx - (long long)b * HW);
+    float K[9], Xw[3], Xs[3], P[3];
+    for (int r = 0; r < 3; r++)
+        for (int k = 0; k < 3; k++) K[r * 3 + k] = camera[b * cbs + r * crs + k];
+    for (int j = 0; j < 3; j++) Xw[j] = X[((size_t)b * 3 + j) * HW + pix];
+    if (pose34) {
+        const float* Rt = pose34 + (size_t)b * 12;
+        for (int j = 0; j < 3; j++)
+            Xs[j] = __fadd_rn(exact::dot3(Rt[4 * j], Rt[4 * j + 1], Rt[4 * j + 2], Xw[0], Xw[1], Xw[2]), Rt[4 * j + 3]);
+    } else {
+        for (int j = 0; j < 3; j++) Xs[j] = Xw[j];
+    }
+    for (int j = 0; j < 3; j++) P[j] = exact::dot3(K[3 * j], K[3 * j + 1], K[3 * j + 2], Xs[0], Xs[1], Xs[2]);
+    float Z = fmaxf(P[2], 1e-5f);
+    float ax = __fdiv_rn(P[0], Z), ay = __fdiv_rn(P[1], Z);
+    coords[idx * 2] = __fadd_rn(__fdiv_rn(__fadd_rn(ax, ax), (float)(W - 1)), -1.0f);
+    coords[idx * 2 + 1] = __fadd_rn(__fdiv_rn(__fadd_rn(ay, ay), (float)(H - 1)), -1.0f);
+}
+
+static int check_problem(const MgvsProblem* p)
+{
+    if (!p) return fail(MGVS_EINVAL, "null problem");
+    if (p->B < 1 || p->H < 3 || p->W < 3 || p->n < 1 || p->n > MGVS_MAX_SCALES) return fail(MGVS_EINVAL, "bad dims (need B>=1, H,W>=3, 1<=n<=8)");
+    if ((long long)p->H * p->W * 3 >= (1ll << 31)) return fail(MGVS_EINVAL, "image plane too large for 32-bit indexing");
+    if (!p->target || !p->source[0] || !p->source[1] || !p->camera || !p->poses) return fail(MGVS_EINVAL, "null input pointer");
+    for (int i = 0; i < p->n; i++)
+        if (!p->inv_depth[i]) return fail(MGVS_EINVAL, "null inverse-depth pointer");
+    if (p->padding_mode != 0) return fail(MGVS_EUNSUPPORTED, "padding_mode: only 'zeros' is implemented");
+    if (p->reduce_op != 0) return fail(MGVS_EUNSUPPORTED, "photometric_reduce_op: only 'min' is implemented");
+    if (!(p->ssim_weight > 0.f)) return fail(MGVS_EUNSUPPORTED, "ssim_loss_weight must be > 0 (the L1-only branch of loss.py:195-196 is not implemented)");
+    if (!p->workspace || ((uintptr_t)p->workspace & 255)) return fail(MGVS_EINVAL, "workspace null or not 256-byte aligned");
+    if (p->workspace_bytes < make_layout(p->B, p->H, p->W, p->n).total) return fail(MGVS_EWORKSPACE, "workspace too small");
+    return MGVS_OK;
+}
+
+static int check_launch(const char* what)
+{
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) {
+        snprintf(g_err, sizeof(g_err), "%s: %s", what, cudaGetErrorString(e));
+        return MGVS_ECUDA;
+    }
+    return MGVS_OK;
+}
+
+}  // namespace mgvs
+
+using namespace mgvs;
+
+extern "C" {
+
+int mgvs_abi_version(void) { return MGVS_ABI_VERSION; }
+const char* mgvs_last_error(void) { return g_err; }
+int mgvs_num_sums(int n) { return 3 * n + 3; }
+
+size_t mgvs_workspace_bytes(int B, int H, int W, int n)
+{
+    if (B < 1 || H < 1 || W < 1 || n < 1 || n > MGVS_MAX_SCALES) return 0;
+    return make_layout(B, H, W, n).total;
+}
+
+int mgvs_forward(const MgvsProblem* p, unsigned char* sel, double* sums, void* cuda_stream)
+{
+    int rc = check_problem(p);
+    if (rc) return rc;
+    if (!sums) return fail(MGVS_EINVAL, "null sums");
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    Layout L = make_layout(p->B, p->H, p->W, p->n);
+    char* ws = (char*)p->workspace;
+    Cam* cams = (Cam*)(ws + L.cams);
+    cudaMemsetAsync(ws + L.counter, 0, 256, st);   // arrival counter of reduce_kernel (workspace arrives uninitialised)
+    prep_kernel<<<(p->B + 63) / 64, 64, 0, st>>>(p->B, p->camera, p->cam_batch_stride, p->cam_row_stride, p->poses, cams);
+    FwdParams fp;
+    memset(&fp, 0, sizeof(fp));
+    fp.B = p->B; fp.H = p->H; fp.W = p->W; fp.n = p->n; fp.automask = p->automask;
+    fp.tgt = p->target; fp.src[0] = p->source[0]; fp.src[1] = p->source[1];
+    for (int i = 0; i < p->n; i++) fp.inv[i] = p->inv_depth[i];
+    fp.mask = p->mask; fp.cams = cams; fp.sel = sel;
+    fp.partials = (double*)(ws + L.partials);
+    fp.alpha = p->ssim_weight; fp.oma = p->one_minus_ssim_weight;
+    fp.tiles_x = L.tiles_x; fp.tiles_y = L.tiles_y;
+    cudaFuncSetAttribute(fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FWD_SMEM_BYTES);
+    fwd_kernel<<<L.tiles, NT, FWD_SMEM_BYTES, st>>>(fp);
+    reduce_kernel<<<p->B, 256, 0, st>>>(p->B, p->n, L.tiles_x * L.tiles_y, (long long)p->H * p->W, fp.partials,
+                                        (double*)(ws + L.imgsums), (unsigned int*)(ws + L.counter), sums);
+    return check_launch("mgvs_forward");
+}
+
+int mgvs_finalize(const MgvsProblem* p, const double* sums, float* losses, void* cuda_stream)
+{
+    if (!p || !sums || !losses) return fail(MGVS_EINVAL, "null argument");
+    if (p->n < 1 || p->n > MGVS_MAX_SCALES) return fail(MGVS_EINVAL, "bad n");
+    finalize_kernel<<<1, 32, 0, (cudaStream_t)cuda_stream>>>(p->n, sums, p->photometric_weight, p->smoothing_weight, losses);
+    return check_launch("mgvs_finalize");
+}
+
+int mgvs_backward(const MgvsProblem* p, const unsigned char* sel, const double* sums, const float* g_losses,
+                  float* const* grad_inv, float* grad_poses, void* cuda_stream)
+{
+    int rc = check_problem(p);
+    if (rc) return rc;
+    if (!sel || !sums || !g_losses || !grad_inv || !grad_poses) return fail(MGVS_EINVAL, "null argument");
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    Layout L = make_layout(p->B, p->H, p->W, p->n);
+    char* ws = (char*)p->workspace;
+    BwdParams bp;
+    memset(&bp, 0, sizeof(bp));
+    bp.B = p->B; bp.H = p->H; bp.W = p->W; bp.n = p->n; bp.automask = p->automask;
+    bp.tgt = p->target; bp.src[0] = p->source[0]; bp.src[1] = p->source[1];
+    for (int i = 0; i < p->n; i++) {
+        bp.inv[i] = p->inv_depth[i];
+        if (!grad_inv[i]) return fail(MGVS_EINVAL, "null grad_inv pointer");
+        bp.grad_inv[i] = grad_inv[i];
+    }
+    bp.mask = p->mask; bp.cams = (const Cam*)(ws + L.cams); bp.sel = sel; bp.sums = sums;
+    bp.imgsums = (const double*)(ws + L.imgsums); bp.g_losses = g_losses;
+    bp.pose_partials = (float*)(ws + L.pose_partials);
+    bp.alpha = p->ssim_weight; bp.oma = p->one_minus_ssim_weight;
+    bp.photo_w = p->photometric_weight; bp.smooth_w = p->smoothing_weight;
+    bp.tiles_x = L.tiles_x; bp.tiles_y = L.tiles_y;
+    cudaFuncSetAttribute(bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, BWD_SMEM_BYTES);
+    bwd_kernel<<<L.tiles, NT, BWD_SMEM_BYTES, st>>>(bp);
+    pose_reduce_kernel<<<p->B * S, 128, 0, st>>>(L.tiles_x * L.tiles_y, bp.pose_partials, p->poses, grad_poses);
+    return check_launch("mgvs_backward");
+}
+
+int mgvs_view_synthesis(int B, int H, int W, const float* ref_image, const float* depth, const float* camera,
+                        long long cam_batch_stride, long long cam_row_stride, const float* pose34, float* warped,
+                        float* coords, void* cuda_stream)
+{
+    if (B < 1 || H < 2 || W < 2 || !ref_image || !depth || !camera || !pose34 || !warped) return fail(MGVS_EINVAL, "bad argument");
+    long long total = (long long)B * H * W;
+    view_synthesis_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)cuda_stream>>>(
+        B, H, W, ref_image, depth, camera, cam_batch_stride, cam_row_stride, pose34, warped, coords);
+    return check_launch("mgvs_view_synthesis");
+}
+
+int mgvs_reconstruct(int B, int H, int W, const float* depth, const float* camera, long long cam_batch_stride,
+                     long long cam_row_stride, float* points, void* cuda_stream)
+{
+    if (B < 1 || H < 1 || W < 1 || !depth || !camera || !points) return fail(MGVS_EINVAL, "bad argument");
+    long long total = (long long)B * H * W;
+    reconstruct_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)cuda_stream>>>(
+        B, H, W, depth, camera, cam_batch_stride, cam_row_stride, points);
+    return check_launch("mgvs_reconstruct");
+}
+
+int mgvs_project(int B, int H, int W, const float* points, const float* camera, long long cam_batch_stride,
+                 long long cam_row_stride, const float* pose34, float* coords, void* cuda_stream)
+{
+    if (B < 1 || H < 2 || W < 2 || !points || !camera || !coords) return fail(MGVS_EINVAL, "bad argument");
+    long long total = (long long)B * H * W;
+    project_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)cuda_stream>>>(
+        B, H, W, points, camera, cam_batch_stride, cam_row_stride, pose34, coords);
+    return check_launch("mgvs_project");
+}
+
+int mgvs_test_div(const float* a, const float* b, float* out, long long count, void* cuda_stream)
+{
+    if (!a || !b || !out || count < 0) return fail(MGVS_EINVAL, "bad argument");
+    test_div_kernel<<<(unsigned)((count + 255) / 256), 256, 0, (cudaStream_t)cuda_stream>>>(a, b, out, count);
+    return check_launch("mgvs_test_div");
+}
+
+}  // extern "C"

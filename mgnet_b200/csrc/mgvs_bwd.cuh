@@ -1,0 +1,405 @@
+// mgvs_bwd.cuh -- fused backward kernel of the view-synthesis loss.
+//
+// Recomputes the forward from the same tiles (nothing but the uint8 selection and a handful of
+// per-image scalars is carried over from the forward pass) and emits
+//   * per-pixel inverse-depth gradients for every scale (each pixel written exactly once), and
+//   * per-tile partial sums of dL/d(R|t) for both sources, reduced later in fixed order
+//     (warp shuffle -> smem -> per-tile store -> pose_reduce_kernel; no float atomics).
+//
+// Per scale, one CTA (64x16 outputs) runs
+//   A  warp both sources on tile+2 (exact forward arithmetic)                              -> smem
+//   B  for every p on tile+1 whose argmin is a warped source: SSIM statistics of THAT source
+//      (bit-identical to the forward, so the clamp decisions agree) -> the three coefficient maps
+//      of the closed-form SSIM adjoint, one channel at a time               -> smem
+//   C  4 outputs per thread: weighted 3x3 box adjoint (reflect-pad multiplicities) of the maps
+//   D  L1 term, bilinear-sample adjoint, projection adjoint, depth gradient, pose partial sums,
+//      plus the smoothness gradient
+#pragma once
+#include "mgvs_device.cuh"
+
+namespace mgvs {
+
+struct BwdParams {
+    int B, H, W, n, automask;
+    const float* tgt;
+    const float* src[S];
+    const float* inv[MAXN];
+    const unsigned char* mask;
+    const Cam* cams;
+    const unsigned char* sel;     // [n,B,H,W]
+    const double* sums;           // [3n+3] global sums (N at [n], Nx at [3n+1], Ny at [3n+2])
+    const double* imgsums;        // [B][4n+3] per-image sums from the forward (photo|smx|smy|invsum|N|Nx|Ny)
+    const float* g_losses;        // [2]
+    float* grad_inv[MAXN];
+    float* pose_partials;         // [tiles][S*12]
+    float alpha, oma, photo_w, smooth_w;
+    int tiles_x, tiles_y;
+};
+
+constexpr int BWD_ROWS = TH + 4;                 // tile+2 halo rows
+constexpr int BWD_CH = BWD_ROWS * PITCH;
+constexpr int BWD_W2 = TW + 4;                   // tile+2 halo width; smem col j <-> image col x0-2+j
+constexpr int BWD_PROWS = TH + 2;                // tile+1 rows (coefficient maps)
+constexpr int BWD_PW = TW + 2;
+constexpr int BWD_MAP = BWD_PROWS * PITCH;       // one coefficient map; col j <-> image col x0-2+j (like fwd)
+constexpr int BWD_PIT = (BWD_PROWS * BWD_PW + NT - 1) / NT;   // stage-B iterations per thread
+constexpr int BWD_SMEM_FLOATS = 3 * BWD_CH + S * 3 * BWD_CH + S * 3 * BWD_MAP + 8 * 24 + 48 + 4 * MAXN;
+constexpr int BWD_SMEM_BYTES = BWD_SMEM_FLOATS * 4;
+
+__device__ __forceinline__ void bwd_load_tile(const float* __restrict__ img, float* __restrict__ dst, int x0, int y0,
+                                              int H, int W, int tid)
+{
+    const int HW = H * W;
+    for (int idx = tid; idx < 3 * BWD_ROWS * BWD_W2; idx += NT) {
+        int ch = idx / (BWD_ROWS * BWD_W2);
+        int r = idx - ch * (BWD_ROWS * BWD_W2);
+        int hr = r / BWD_W2, hc = r - hr * BWD_W2;
+        int v = reflect_idx(y0 - 2 + hr, H), u = reflect_idx(x0 - 2 + hc, W);
+        dst[ch * BWD_CH + hr * PITCH + hc] = __ldg(img + ch * HW + v * W + u);
+    }
+}
+
+__global__ void __launch_bounds__(NT, 2) bwd_kernel(const BwdParams p)
+{
+    extern __shared__ __align__(16) float smem[];
+    float* sY = smem;                               // [3][BWD_ROWS][PITCH]
+    float* sX = sY + 3 * BWD_CH;                    // [S][3][BWD_ROWS][PITCH]
+    float* sCo = sX + S * 3 * BWD_CH;               // [S][3 maps][BWD_PROWS][PITCH]  (one channel at a time)
+    float* sRed = sCo + S * 3 * BWD_MAP;            // [8 warps][24]
+    float* sCam = sRed + 8 * 24;                    // 48
+    float* sSm = sCam + 48;                         // [n][4]: inv_c/Nx-scale, inv_c/Ny-scale, mean_term, unused
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tile = blockIdx.x;
+    const int tpi = p.tiles_x * p.tiles_y;
+    const int b = tile / tpi;
+    const int trem = tile - b * tpi;
+    const int tyi = trem / p.tiles_x, txi = trem - tyi * p.tiles_x;
+    const int x0 = txi * TW, y0 = tyi * TH;
+    const int H = p.H, W = p.W, HW = H * W;
+    const int tx = tid & 15, ty = tid >> 4;
+    const int u0 = x0 + 4 * tx, v = y0 + ty;
+
+    if (tid < 48) sCam[tid] = reinterpret_cast<const float*>(p.cams + b)[tid];
+    const int nq = 4 * p.n + 3;
+    const double Ntot = p.sums[p.n], Nx = p.sums[3 * p.n + 1], Ny = p.sums[3 * p.n + 2];
+    const float g_photo = __ldg(p.g_losses), g_smooth = __ldg(p.g_losses + 1);
+    if (tid < p.n) {
+        // smoothness constants of (image b, scale tid): SURVEY App. B-6
+        const double* is = p.imgsums + (size_t)b * nq;
+        double mean = is[3 * p.n + tid] / (double)HW;
+        bool active = mean >= 1e-6;
+        double c = active ? mean : 1e-6;
+        double Ws = (double)g_smooth * (double)p.smooth_w / ((double)p.n * (double)(1 << tid));
+        double A = is[p.n + tid] / Nx + is[2 * p.n + tid] / Ny;     // un-normalised sums / counts
+        sSm[tid * 4 + 0] = (float)(Ws / (Nx * c));
+        sSm[tid * 4 + 1] = (float)(Ws / (Ny * c));
+        sSm[tid * 4 + 2] = active ? (float)(-Ws * A / (c * c * (double)HW)) : 0.f;
+    }
+    bwd_load_tile(p.tgt + (size_t)b * 3 * HW, sY, x0, y0, H, W, tid);
+    __syncthreads();
+
+    const float* K = sCam;
+    const float* Kinv = sCam + 9;
+    const float wm1 = (float)(W - 1), hm1 = (float)(H - 1);
+    const float rw = exact::rcp_refined(wm1), rh = exact::rcp_refined(hm1);
+    const float Wp = (float)((double)g_photo * (double)p.photo_w / ((double)p.n * Ntot));
+    const float cf_ssim = Wp * p.alpha * (1.0f / 3.0f) * (-0.5f) * (1.0f / 9.0f);   // u/9 of App. B-3
+    const float cf_l1 = Wp * p.oma * (1.0f / 3.0f);
+
+    const float* src0 = p.src[0] + (size_t)b * 3 * HW;
+    const float* src1 = p.src[1] + (size_t)b * 3 * HW;
+
+    bool valid[4], msk[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        valid[k] = (v < H) && (u0 + k < W);
+        msk[k] = valid[k] && (p.mask == nullptr || p.mask[(size_t)b * HW + (size_t)min(v, H - 1) * W + min(u0 + k, W - 1)] != 0);
+    }
+    // reflect-pad multiplicities of the box adjoint: tap (q+d) counts twice when its padded twin folds onto q
+    float rwgt[3], cwgt[4][3];
+    rwgt[0] = (v - 1 >= 0) ? ((v == 1) ? 2.f : 1.f) : 0.f;
+    rwgt[1] = 1.f;
+    rwgt[2] = (v + 1 <= H - 1) ? ((v == H - 2) ? 2.f : 1.f) : 0.f;
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        int u = u0 + k;
+        cwgt[k][0] = (u - 1 >= 0) ? ((u == 1) ? 2.f : 1.f) : 0.f;
+        cwgt[k][1] = 1.f;
+        cwgt[k][2] = (u + 1 <= W - 1) ? ((u == W - 2) ? 2.f : 1.f) : 0.f;
+    }
+
+    float pacc[S][12];
+#pragma unroll
+    for (int s = 0; s < S; s++)
+#pragma unroll
+        for (int j = 0; j < 12; j++) pacc[s][j] = 0.f;
+
+    for (int i = 0; i < p.n; i++) {
+        const float* inv = p.inv[i] + (size_t)b * HW;
+        const unsigned char* sel = p.sel + ((size_t)i * p.B + b) * HW;
+
+        // ---- stage A: warp both sources on tile+2 ----
+        for (int h = tid; h < BWD_ROWS * BWD_W2; h += NT) {
+            int hr = h / BWD_W2, hc = h - hr * BWD_W2;
+            int pv = reflect_idx(y0 - 2 + hr, H), pu = reflect_idx(x0 - 2 + hc, W);
+            float r[3], Xc[3];
+            exact::ray(Kinv, pu, pv, r);
+            float d = exact::rcp_refined(fmaxf(__ldg(inv + pv * W + pu), 1e-6f));
+#pragma unroll
+            for (int j = 0; j < 3; j++) Xc[j] = __fmul_rn(r[j], d);
+#pragma unroll
+            for (int s = 0; s < S; s++) {
+                exact::Proj pr;
+                exact::project(K, sCam + 18 + 12 * s, Xc, wm1, hm1, rw, rh, pr);
+                exact::Cell c;
+                exact::cell(pr.ix, pr.iy, H, W, c);
+                float wnw = __fmul_rn(c.wN, c.wW), wne = __fmul_rn(c.wN, c.wE), wsw = __fmul_rn(c.wS, c.wW),
+                      wse = __fmul_rn(c.wS, c.wE);
+                const float* sp = s == 0 ? src0 : src1;
+                float* dst = sX + s * 3 * BWD_CH + hr * PITCH + hc;
+#pragma unroll
+                for (int ch = 0; ch < 3; ch++) {
+                    float vals[4];
+                    dst[ch * BWD_CH] = exact::blend(sp + ch * HW, W, c, wnw, wne, wsw, wse, vals);
+                }
+            }
+        }
+        // which source (0/1) is selected at each of my stage-B pixels; 2 = none
+        unsigned char psel[BWD_PIT];
+#pragma unroll
+        for (int it = 0; it < BWD_PIT; it++) {
+            int h = tid + it * NT;
+            unsigned char code = 2;
+            if (h < BWD_PROWS * BWD_PW) {
+                int pr = h / BWD_PW, pc = h - pr * BWD_PW;
+                int pv = y0 - 1 + pr, pu = x0 - 1 + pc;
+                if (pv >= 0 && pv < H && pu >= 0 && pu < W) {
+                    bool m = p.mask == nullptr || p.mask[(size_t)b * HW + (size_t)pv * W + pu] != 0;
+                    unsigned k = sel[(size_t)pv * W + pu];
+                    if (m) {
+                        if (p.automask) { if ((k & 1u) == 0) code = (unsigned char)(k >> 1); }
+                        else code = (unsigned char)k;
+                    }
+                }
+            }
+            psel[it] = code;
+        }
+        __syncthreads();
+
+        float G[S][3][4];
+#pragma unroll
+        for (int ch = 0; ch < 3; ch++) {
+            // ---- stage B: coefficient maps of channel ch ----
+#pragma unroll
+            for (int it = 0; it < BWD_PIT; it++) {
+                int h = tid + it * NT;
+                if (h < BWD_PROWS * BWD_PW) {
+                    int pr = h / BWD_PW, pc = h - pr * BWD_PW;
+                    float ca = 0.f, cb = 0.f, cc = 0.f;
+                    unsigned s = psel[it];
+                    if (s < 2) {
+                        // window rows pr..pr+2, cols pc..pc+2 in tile+2 coordinates
+                        const float* xw = sX + s * 3 * BWD_CH + ch * BWD_CH + pr * PITCH + pc;
+                        const float* yw = sY + ch * BWD_CH + pr * PITCH + pc;
+                        float sx, sxx, sxy, sy, syy;
+#pragma unroll
+                        for (int dy = 0; dy < 3; dy++)
+#pragma unroll
+                            for (int dx = 0; dx < 3; dx++) {
+                                float xv = xw[dy * PITCH + dx], yv = yw[dy * PITCH + dx];
+                                float xx = __fmul_rn(xv, xv), xy = __fmul_rn(xv, yv), yy = __fmul_rn(yv, yv);
+                                if (dy == 0 && dx == 0) { sx = xv; sxx = xx; sxy = xy; sy = yv; syy = yy; }
+                                else {
+                                    sx = __fadd_rn(sx, xv); sxx = __fadd_rn(sxx, xx); sxy = __fadd_rn(sxy, xy);
+                                    sy = __fadd_rn(sy, yv); syy = __fadd_rn(syy, yy);
+                                }
+                            }
+                        float mu_y = exact::div9(sy);
+                        float mys = __fmul_rn(mu_y, mu_y);
+                        float sgy = __fadd_rn(exact::div9(syy), -mys);
+                        exact::Ssim q;
+                        (void)exact::ssim_from_sums(sx, sxx, sxy, mu_y, mys, sgy, &q);
+                        if (q.loss_raw >= 0.f && q.loss_raw <= 1.f) {      // clamp passes gradient inclusively
+                            float id1 = 1.0f / q.d1, id2 = 1.0f / q.d2;
+                            float idd = id1 * id2;
+                            float ds_dmux = 2.f * mu_y * (q.n2 - q.n1) * idd - q.ssim * 2.f * q.mu_x * (id1 - id2);
+                            float ds_dexx = -q.ssim * id2;
+                            float ds_dexy = 2.f * q.n1 * idd;
+                            ca = cf_ssim * ds_dmux;
+                            cb = cf_ssim * 2.f * ds_dexx;
+                            cc = cf_ssim * ds_dexy;
+                        }
+                    }
+                    float* m0 = sCo + pr * PITCH + pc + 1;               // set 0
+                    float* m1 = m0 + 3 * BWD_MAP;                        // set 1
+                    bool s0 = (s == 0), s1 = (s == 1);
+                    m0[0] = s0 ? ca : 0.f; m0[BWD_MAP] = s0 ? cb : 0.f; m0[2 * BWD_MAP] = s0 ? cc : 0.f;
+                    m1[0] = s1 ? ca : 0.f; m1[BWD_MAP] = s1 ? cb : 0.f; m1[2 * BWD_MAP] = s1 ? cc : 0.f;
+                }
+            }
+            __syncthreads();
+            // ---- stage C: weighted 3x3 box adjoint for my 4 outputs ----
+#pragma unroll
+            for (int s = 0; s < S; s++) {
+                float box[3][4];
+#pragma unroll
+                for (int m = 0; m < 3; m++) {
+                    const float* mp = sCo + (s * 3 + m) * BWD_MAP + ty * PITCH + 4 * tx;
+                    float col[6] = {0, 0, 0, 0, 0, 0};
+#pragma unroll
+                    for (int dy = 0; dy < 3; dy++) {
+                        const float4* rr = reinterpret_cast<const float4*>(mp + dy * PITCH);
+                        float4 a = rr[0], bq = rr[1];
+                        float r6[6] = {a.y, a.z, a.w, bq.x, bq.y, bq.z};
+#pragma unroll
+                        for (int j = 0; j < 6; j++) col[j] = fmaf(rwgt[dy], r6[j], col[j]);
+                    }
+#pragma unroll
+                    for (int k = 0; k < 4; k++)
+                        box[m][k] = cwgt[k][0] * col[k] + cwgt[k][1] * col[k + 1] + cwgt[k][2] * col[k + 2];
+                }
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    float xq = sX[s * 3 * BWD_CH + ch * BWD_CH + (ty + 2) * PITCH + 4 * tx + 2 + k];
+                    float yq = sY[ch * BWD_CH + (ty + 2) * PITCH + 4 * tx + 2 + k];
+                    G[s][ch][k] = box[0][k] + xq * box[1][k] + yq * box[2][k];
+                }
+            }
+            __syncthreads();   // maps free for the next channel
+        }
+
+        // ---- stage D: per-output chain ----
+        float ginv[4];
+        unsigned selq = 0;
+        if (v < H) {
+#pragma unroll
+            for (int k = 0; k < 4; k++) if (u0 + k < W) selq |= (unsigned)sel[(size_t)v * W + u0 + k] << (8 * k);
+        }
+        // smoothness gradient (App. B-6): d/dinv of sum m*w*|inv_p - inv_q| / (N*c) plus the mean term
+        {
+            const float kx = sSm[i * 4 + 0], ky = sSm[i * 4 + 1], mt = sSm[i * 4 + 2];
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                float g = 0.f;
+                int u = u0 + k;
+                if (valid[k]) {
+                    g = mt;
+                    const float* yc = sY + (ty + 2) * PITCH + 4 * tx + 2 + k;
+                    float ic = __ldg(inv + (size_t)v * W + u);
+                    // pair (p, p+1): owner mask is the LEFT pixel (loss.py:285)
+                    if (u + 1 < W && msk[k]) {
+                        float a = fabsf(yc[0] - yc[1]) + fabsf(yc[BWD_CH] - yc[BWD_CH + 1]) + fabsf(yc[2 * BWD_CH] - yc[2 * BWD_CH + 1]);
+                        float w = expf(-exact::div3(a));
+                        float df = ic - __ldg(inv + (size_t)v * W + u + 1);
+                        g += kx * w * (df > 0.f ? 1.f : (df < 0.f ? -1.f : 0.f));
+                    }
+                    if (u > 0 && (p.mask == nullptr || p.mask[(size_t)b * HW + (size_t)v * W + u - 1] != 0)) {
+                        float a = fabsf(yc[-1] - yc[0]) + fabsf(yc[BWD_CH - 1] - yc[BWD_CH]) + fabsf(yc[2 * BWD_CH - 1] - yc[2 * BWD_CH]);
+                        float w = expf(-exact::div3(a));
+                        float df = __ldg(inv + (size_t)v * W + u - 1) - ic;
+                        g -= kx * w * (df > 0.f ? 1.f : (df < 0.f ? -1.f : 0.f));
+                    }
+                    if (v + 1 < H && msk[k]) {
+                        float a = fabsf(yc[0] - yc[PITCH]) + fabsf(yc[BWD_CH] - yc[BWD_CH + PITCH]) + fabsf(yc[2 * BWD_CH] - yc[2 * BWD_CH + PITCH]);
+                        float w = expf(-exact::div3(a));
+                        float df = ic - __ldg(inv + (size_t)(v + 1) * W + u);
+                        g += ky * w * (df > 0.f ? 1.f : (df < 0.f ? -1.f : 0.f));
+                    }
+                    if (v > 0 && (p.mask == nullptr || p.mask[(size_t)b * HW + (size_t)(v - 1) * W + u] != 0)) {
+                        float a = fabsf(yc[-PITCH] - yc[0]) + fabsf(yc[BWD_CH - PITCH] - yc[BWD_CH]) + fabsf(yc[2 * BWD_CH - PITCH] - yc[2 * BWD_CH]);
+                        float w = expf(-exact::div3(a));
+                        float df = __ldg(inv + (size_t)(v - 1) * W + u) - ic;
+                        g -= ky * w * (df > 0.f ? 1.f : (df < 0.f ? -1.f : 0.f));
+                    }
+                }
+                ginv[k] = g;
+            }
+        }
+#pragma unroll
+        for (int s = 0; s < S; s++) {
+            const float* Rt = sCam + 18 + 12 * s;
+            const float* sp = s == 0 ? src0 : src1;
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                if (!valid[k]) continue;
+                unsigned code = (selq >> (8 * k)) & 0xffu;
+                bool selme = msk[k] && (p.automask ? (code == 2u * s) : (code == (unsigned)s));
+                float g0 = G[s][0][k], g1 = G[s][1][k], g2 = G[s][2][k];
+                if (selme) {
+                    const float* xq = sX + s * 3 * BWD_CH + (ty + 2) * PITCH + 4 * tx + 2 + k;
+                    const float* yq = sY + (ty + 2) * PITCH + 4 * tx + 2 + k;
+                    float d0 = xq[0] - yq[0], d1 = xq[BWD_CH] - yq[BWD_CH], d2 = xq[2 * BWD_CH] - yq[2 * BWD_CH];
+                    g0 += cf_l1 * (d0 > 0.f ? 1.f : (d0 < 0.f ? -1.f : 0.f));
+                    g1 += cf_l1 * (d1 > 0.f ? 1.f : (d1 < 0.f ? -1.f : 0.f));
+                    g2 += cf_l1 * (d2 > 0.f ? 1.f : (d2 < 0.f ? -1.f : 0.f));
+                }
+                if (g0 == 0.f && g1 == 0.f && g2 == 0.f) continue;
+                int u = u0 + k;
+                float r[3], Xc[3];
+                exact::ray(Kinv, u, v, r);
+                float invq = __ldg(inv + (size_t)v * W + u);
+                float d = exact::rcp_refined(fmaxf(invq, 1e-6f));
+#pragma unroll
+                for (int j = 0; j < 3; j++) Xc[j] = __fmul_rn(r[j], d);
+                exact::Proj pr;
+                exact::project(K, Rt, Xc, wm1, hm1, rw, rh, pr);
+                exact::Cell c;
+                exact::cell(pr.ix, pr.iy, H, W, c);
+                float gix = 0.f, giy = 0.f;
+                const float gch[3] = {g0, g1, g2};
+#pragma unroll
+                for (int ch = 0; ch < 3; ch++) {
+                    const float* pl = sp + ch * HW + c.off;
+                    float nw = c.nw ? __ldg(pl) : 0.f, ne = c.ne ? __ldg(pl + 1) : 0.f;
+                    float sw = c.sw ? __ldg(pl + W) : 0.f, se = c.se ? __ldg(pl + W + 1) : 0.f;
+                    gix += gch[ch] * ((ne - nw) * c.wN + (se - sw) * c.wS);
+                    giy += gch[ch] * ((sw - nw) * c.wW + (se - ne) * c.wE);
+                }
+                // projection adjoint (App. B-5)
+                float iz = 1.0f / pr.Z;
+                float gP0 = gix * iz, gP1 = giy * iz;
+                float gP2 = (pr.Pz >= 1e-5f) ? -(gix * pr.ax + giy * pr.ay) * iz : 0.f;
+                float gX0 = K[0] * gP0 + K[3] * gP1 + K[6] * gP2;
+                float gX1 = K[1] * gP0 + K[4] * gP1 + K[7] * gP2;
+                float gX2 = K[2] * gP0 + K[5] * gP1 + K[8] * gP2;
+                pacc[s][0] += gX0 * pr.Xc0; pacc[s][1] += gX0 * pr.Xc1; pacc[s][2] += gX0 * pr.Xc2; pacc[s][3] += gX0;
+                pacc[s][4] += gX1 * pr.Xc0; pacc[s][5] += gX1 * pr.Xc1; pacc[s][6] += gX1 * pr.Xc2; pacc[s][7] += gX1;
+                pacc[s][8] += gX2 * pr.Xc0; pacc[s][9] += gX2 * pr.Xc1; pacc[s][10] += gX2 * pr.Xc2; pacc[s][11] += gX2;
+                float gd = 0.f;
+#pragma unroll
+                for (int j = 0; j < 3; j++) gd += (Rt[j] * gX0 + Rt[4 + j] * gX1 + Rt[8 + j] * gX2) * r[j];
+                if (invq >= 1e-6f) ginv[k] -= d * d * gd;
+            }
+        }
+        if (v < H) {
+            float* go = p.grad_inv[i] + (size_t)b * HW + (size_t)v * W + u0;
+            if (u0 + 3 < W && ((W & 3) == 0)) *reinterpret_cast<float4*>(go) = make_float4(ginv[0], ginv[1], ginv[2], ginv[3]);
+            else {
+#pragma unroll
+                for (int k = 0; k < 4; k++) if (u0 + k < W) go[k] = ginv[k];
+            }
+        }
+        // (the next scale's stage A overwrites sX: every reader of sX in stage D is done only after
+        //  this barrier)
+        __syncthreads();
+    }
+
+    // deterministic pose partials: shuffle tree -> smem -> fixed-order sum -> one store per tile
+#pragma unroll
+    for (int s = 0; s < S; s++)
+#pragma unroll
+        for (int j = 0; j < 12; j++) {
+            float vsum = warp_sum(pacc[s][j]);
+            if (lane == 0) sRed[warp * 24 + s * 12 + j] = vsum;
+        }
+    __syncthreads();
+    if (tid < 24) {
+        float acc = 0.f;
+#pragma unroll
+        for (int w = 0; w < NT / 32; w++) acc += sRed[w * 24 + tid];
+        p.pose_partials[(size_t)tile * 24 + tid] = acc;
+    }
+}
+
+}  // namespace mgvs

@@ -1,0 +1,304 @@
+// mgvs_fwd.cuh -- fused forward kernel of the view-synthesis loss (one launch per call).
+//
+// One CTA owns a 64x16 tile of target pixels of one image and loops over all n scales:
+//   stage 0  target tile + 1-pixel SSIM halo (reflect indexed) and both source tiles -> smem;
+//            per-pixel target statistics (mu_y, mu_y^2, sigma_y) -> smem; identity-reprojection
+//            losses of both sources -> registers (computed once, reused by every scale; loss.py:139-144)
+//   stage 1  (per scale) every halo pixel: K^-1 back-projection, SE(3), projection, bilinear gather of
+//            both sources -> smem (the warped images never reach HBM)
+//   stage 2  (per scale) 4 horizontally adjacent outputs per thread: 3x3 SSIM + L1 against the target,
+//            min / argmin over [warp_prev, id_prev, warp_next, id_next], masked sum, smoothness terms
+//   stage 3  deterministic CTA reduction -> per-tile partial sums (fp64) for the finalise pass
+#pragma once
+#include "mgvs_device.cuh"
+
+namespace mgvs {
+
+struct FwdParams {
+    int B, H, W, n, automask;
+    const float* tgt;
+    const float* src[S];
+    const float* inv[MAXN];
+    const unsigned char* mask;   // may be null
+    const Cam* cams;
+    unsigned char* sel;          // may be null
+    double* partials;            // [tiles][4n+3]
+    float alpha, oma;
+    int tiles_x, tiles_y;
+};
+
+constexpr int FWD_ROWS = TH + 2;                 // halo rows
+constexpr int FWD_CH = FWD_ROWS * PITCH;         // floats per channel plane in smem
+constexpr int FWD_HALO_W = TW + 2;
+constexpr int FWD_SMEM_FLOATS = 3 * FWD_CH /*Y*/ + S * 3 * FWD_CH /*X*/ + 9 * TH * TW /*Y stats*/ + 8 * 8 /*red*/ + 48 /*cam*/;
+constexpr int FWD_SMEM_BYTES = FWD_SMEM_FLOATS * 4;
+
+// Loads a [3,H,W] image tile with 1-pixel halo (reflect-indexed) into smem planes.
+__device__ __forceinline__ void fwd_load_tile(const float* __restrict__ img, float* __restrict__ dst, int x0, int y0,
+                                              int H, int W, int tid)
+{
+    const int HW = H * W;
+    for (int idx = tid; idx < 3 * FWD_ROWS * FWD_HALO_W; idx += NT) {
+        int ch = idx / (FWD_ROWS * FWD_HALO_W);
+        int r = idx - ch * (FWD_ROWS * FWD_HALO_W);
+        int hr = r / FWD_HALO_W, hc = r - hr * FWD_HALO_W;
+        int v = reflect_idx(y0 - 1 + hr, H), u = reflect_idx(x0 - 1 + hc, W);
+        dst[ch * FWD_CH + hr * PITCH + 1 + hc] = __ldg(img + ch * HW + v * W + u);
+    }
+}
+
+// Photometric loss (alpha*mean_c SSIM + (1-alpha)*mean_c L1, loss.py:186-194) of 4 adjacent outputs.
+// xs, ys: smem planes of the estimate and the target, pointing at [ch 0][row ty][col 4*tx] (16B aligned);
+// yst: target statistics at [0][ty][4*tx].
+__device__ __forceinline__ void photometric4(const float* __restrict__ xs, const float* __restrict__ ys,
+                                             const float* __restrict__ yst, float alpha, float oma, float out[4])
+{
+    float ssum[4], lsum[4];
+#pragma unroll
+    for (int ch = 0; ch < 3; ch++) {
+        float sx[4], sxx[4], sxy[4], l1[4];
+#pragma unroll
+        for (int dy = 0; dy < 3; dy++) {
+            const float4* xr = reinterpret_cast<const float4*>(xs + ch * FWD_CH + dy * PITCH);
+            const float4* yr = reinterpret_cast<const float4*>(ys + ch * FWD_CH + dy * PITCH);
+            float4 xa = xr[0], xb = xr[1], ya = yr[0], yb = yr[1];
+            // window columns 4tx+1 .. 4tx+6
+            float x6[6] = {xa.y, xa.z, xa.w, xb.x, xb.y, xb.z};
+            float y6[6] = {ya.y, ya.z, ya.w, yb.x, yb.y, yb.z};
+            float xx6[6], xy6[6];
+#pragma unroll
+            for (int j = 0; j < 6; j++) { xx6[j] = __fmul_rn(x6[j], x6[j]); xy6[j] = __fmul_rn(x6[j], y6[j]); }
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                // row-major 9-term sums, left to right (App. A "3x3 mean")
+                if (dy == 0) { sx[k] = x6[k]; sxx[k] = xx6[k]; sxy[k] = xy6[k]; }
+                else { sx[k] = __fadd_rn(sx[k], x6[k]); sxx[k] = __fadd_rn(sxx[k], xx6[k]); sxy[k] = __fadd_rn(sxy[k], xy6[k]); }
+                sx[k] = __fadd_rn(sx[k], x6[k + 1]); sxx[k] = __fadd_rn(sxx[k], xx6[k + 1]); sxy[k] = __fadd_rn(sxy[k], xy6[k + 1]);
+                sx[k] = __fadd_rn(sx[k], x6[k + 2]); sxx[k] = __fadd_rn(sxx[k], xx6[k + 2]); sxy[k] = __fadd_rn(sxy[k], xy6[k + 2]);
+                if (dy == 1) l1[k] = fabsf(__fadd_rn(x6[k + 1], -y6[k + 1]));
+            }
+        }
+        float4 muy = *reinterpret_cast<const float4*>(yst + (ch * 3 + 0) * TH * TW);
+        float4 mys = *reinterpret_cast<const float4*>(yst + (ch * 3 + 1) * TH * TW);
+        float4 sgy = *reinterpret_cast<const float4*>(yst + (ch * 3 + 2) * TH * TW);
+        const float muy4[4] = {muy.x, muy.y, muy.z, muy.w}, mys4[4] = {mys.x, mys.y, mys.z, mys.w},
+                    sgy4[4] = {sgy.x, sgy.y, sgy.z, sgy.w};
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            float l = exact::ssim_from_sums(sx[k], sxx[k], sxy[k], muy4[k], mys4[k], sgy4[k], nullptr);
+            if (ch == 0) { ssum[k] = l; lsum[k] = l1[k]; }
+            else { ssum[k] = __fadd_rn(ssum[k], l); lsum[k] = __fadd_rn(lsum[k], l1[k]); }
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < 4; k++)
+        out[k] = __fadd_rn(__fmul_rn(alpha, exact::div3(ssum[k])), __fmul_rn(oma, exact::div3(lsum[k])));
+}
+
+__global__ void __launch_bounds__(NT, 2) fwd_kernel(const FwdParams p)
+{
+    extern __shared__ __align__(16) float smem[];
+    float* sY = smem;
+    float* sX = sY + 3 * FWD_CH;            // [S][3][rows][PITCH]
+    float* sYst = sX + S * 3 * FWD_CH;      // [9][TH][TW]
+    float* sRed = sYst + 9 * TH * TW;       // [8 warps][8]
+    float* sCam = sRed + 64;                // 48 floats
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tile = blockIdx.x;
+    const int tpi = p.tiles_x * p.tiles_y;
+    const int b = tile / tpi;
+    const int trem = tile - b * tpi;
+    const int tyi = trem / p.tiles_x, txi = trem - tyi * p.tiles_x;
+    const int x0 = txi * TW, y0 = tyi * TH;
+    const int H = p.H, W = p.W, HW = H * W;
+    const int tx = tid & 15, ty = tid >> 4;
+    const int u0 = x0 + 4 * tx, v = y0 + ty;     // this thread's 4 outputs: (v, u0..u0+3)
+
+    if (tid < 48) sCam[tid] = reinterpret_cast<const float*>(p.cams + b)[tid];
+    fwd_load_tile(p.tgt + (size_t)b * 3 * HW, sY, x0, y0, H, W, tid);
+    fwd_load_tile(p.src[0] + (size_t)b * 3 * HW, sX, x0, y0, H, W, tid);
+    fwd_load_tile(p.src[1] + (size_t)b * 3 * HW, sX + 3 * FWD_CH, x0, y0, H, W, tid);
+    __syncthreads();
+
+    const float* K = sCam;
+    const float* Kinv = sCam + 9;
+    const float wm1 = (float)(W - 1), hm1 = (float)(H - 1);
+    const float rw = exact::rcp_refined(wm1), rh = exact::rcp_refined(hm1);
+
+    // validity and mask of the 4 outputs
+    bool valid[4];
+    bool msk[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        valid[k] = (v < H) && (u0 + k < W);
+        msk[k] = valid[k] && (p.mask == nullptr || p.mask[(size_t)b * HW + (size_t)min(v, H - 1) * W + min(u0 + k, W - 1)] != 0);
+    }
+
+    const float* ys_t = sY + ty * PITCH + 4 * tx;
+    float* yst_t = sYst + ty * TW + 4 * tx;
+    // target statistics for my 4 outputs (shared by all 2+2n photometric evaluations)
+#pragma unroll
+    for (int ch = 0; ch < 3; ch++) {
+        float sy[4], syy[4];
+#pragma unroll
+        for (int dy = 0; dy < 3; dy++) {
+            const float4* yr = reinterpret_cast<const float4*>(ys_t + ch * FWD_CH + dy * PITCH);
+            float4 ya = yr[0], yb = yr[1];
+            float y6[6] = {ya.y, ya.z, ya.w, yb.x, yb.y, yb.z}, yy6[6];
+#pragma unroll
+            for (int j = 0; j < 6; j++) yy6[j] = __fmul_rn(y6[j], y6[j]);
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                if (dy == 0) { sy[k] = y6[k]; syy[k] = yy6[k]; }
+                else { sy[k] = __fadd_rn(sy[k], y6[k]); syy[k] = __fadd_rn(syy[k], yy6[k]); }
+                sy[k] = __fadd_rn(sy[k], y6[k + 1]); syy[k] = __fadd_rn(syy[k], yy6[k + 1]);
+                sy[k] = __fadd_rn(sy[k], y6[k + 2]); syy[k] = __fadd_rn(syy[k], yy6[k + 2]);
+            }
+        }
+        float mu[4], ms[4], sg[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            mu[k] = exact::div9(sy[k]);
+            ms[k] = __fmul_rn(mu[k], mu[k]);
+            sg[k] = __fadd_rn(exact::div9(syy[k]), -ms[k]);
+        }
+        *reinterpret_cast<float4*>(yst_t + (ch * 3 + 0) * TH * TW) = make_float4(mu[0], mu[1], mu[2], mu[3]);
+        *reinterpret_cast<float4*>(yst_t + (ch * 3 + 1) * TH * TW) = make_float4(ms[0], ms[1], ms[2], ms[3]);
+        *reinterpret_cast<float4*>(yst_t + (ch * 3 + 2) * TH * TW) = make_float4(sg[0], sg[1], sg[2], sg[3]);
+    }
+    // (each thread only reads back its own statistics: no barrier needed)
+
+    // identity-reprojection losses (un-warped source vs target), once per tile
+    float lid0[4] = {0, 0, 0, 0}, lid1[4] = {0, 0, 0, 0};
+    if (p.automask) {
+        photometric4(sX + ty * PITCH + 4 * tx, ys_t, yst_t, p.alpha, p.oma, lid0);
+        photometric4(sX + 3 * FWD_CH + ty * PITCH + 4 * tx, ys_t, yst_t, p.alpha, p.oma, lid1);
+    }
+
+    // edge-aware smoothness weights exp(-mean_c |dI|) (depth.py:23-24), premultiplied by mask/validity
+    float wxm[4], wym[4];
+    float cntN = 0.f, cntX = 0.f, cntY = 0.f;
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        const float* yc = sY + (ty + 1) * PITCH + 4 * tx + 2 + k;
+        float ax = 0.f, ay = 0.f;
+#pragma unroll
+        for (int ch = 0; ch < 3; ch++) {
+            float c0 = yc[ch * FWD_CH];
+            float dx = fabsf(__fadd_rn(c0, -yc[ch * FWD_CH + 1]));
+            float dyv = fabsf(__fadd_rn(c0, -yc[ch * FWD_CH + PITCH]));
+            ax = ch == 0 ? dx : __fadd_rn(ax, dx);
+            ay = ch == 0 ? dyv : __fadd_rn(ay, dyv);
+        }
+        bool hx = msk[k] && (u0 + k + 1 < W), hy = msk[k] && (v + 1 < H);
+        wxm[k] = hx ? expf(-exact::div3(ax)) : 0.f;
+        wym[k] = hy ? expf(-exact::div3(ay)) : 0.f;
+        cntN += msk[k] ? 1.f : 0.f;
+        cntX += hx ? 1.f : 0.f;
+        cntY += hy ? 1.f : 0.f;
+    }
+    __syncthreads();   // identity evaluation done: sX may be overwritten
+
+    const int nq = 4 * p.n + 3;
+    double* my_partials = p.partials + (size_t)tile * nq;
+    const float* src0 = p.src[0] + (size_t)b * 3 * HW;
+    const float* src1 = p.src[1] + (size_t)b * 3 * HW;
+
+    for (int i = 0; i < p.n; i++) {
+        const float* inv = p.inv[i] + (size_t)b * HW;
+        // ---- stage 1: warp both sources at every halo pixel ----
+        for (int h = tid; h < FWD_ROWS * FWD_HALO_W; h += NT) {
+            int hr = h / FWD_HALO_W, hc = h - hr * FWD_HALO_W;
+            int pv = reflect_idx(y0 - 1 + hr, H), pu = reflect_idx(x0 - 1 + hc, W);
+            float r[3], Xc[3];
+            exact::ray(Kinv, pu, pv, r);
+            float d = exact::rcp_refined(fmaxf(__ldg(inv + pv * W + pu), 1e-6f));   // depth.py:15
+#pragma unroll
+            for (int j = 0; j < 3; j++) Xc[j] = __fmul_rn(r[j], d);
+#pragma unroll
+            for (int s = 0; s < S; s++) {
+                exact::Proj pr;
+                exact::project(K, sCam + 18 + 12 * s, Xc, wm1, hm1, rw, rh, pr);
+                exact::Cell c;
+                exact::cell(pr.ix, pr.iy, H, W, c);
+                float wnw = __fmul_rn(c.wN, c.wW), wne = __fmul_rn(c.wN, c.wE), wsw = __fmul_rn(c.wS, c.wW),
+                      wse = __fmul_rn(c.wS, c.wE);
+                const float* sp = s == 0 ? src0 : src1;
+                float* dst = sX + s * 3 * FWD_CH + hr * PITCH + 1 + hc;
+#pragma unroll
+                for (int ch = 0; ch < 3; ch++) {
+                    float vals[4];
+                    dst[ch * FWD_CH] = exact::blend(sp + ch * HW, W, c, wnw, wne, wsw, wse, vals);
+                }
+            }
+        }
+        __syncthreads();
+
+        // ---- stage 2: photometric maps, min/argmin, smoothness ----
+        float lw0[4], lw1[4];
+        photometric4(sX + ty * PITCH + 4 * tx, ys_t, yst_t, p.alpha, p.oma, lw0);
+        photometric4(sX + 3 * FWD_CH + ty * PITCH + 4 * tx, ys_t, yst_t, p.alpha, p.oma, lw1);
+        float photo = 0.f;
+        unsigned selw = 0;
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            float best = lw0[k];
+            unsigned bi = 0;
+            if (p.automask) {
+                if (lid0[k] < best) { best = lid0[k]; bi = 1; }
+                if (lw1[k] < best) { best = lw1[k]; bi = 2; }
+                if (lid1[k] < best) { best = lid1[k]; bi = 3; }
+            } else {
+                if (lw1[k] < best) { best = lw1[k]; bi = 1; }
+            }
+            if (msk[k]) photo += best;
+            selw |= bi << (8 * k);
+        }
+        if (p.sel != nullptr && v < H) {
+            unsigned char* sp = p.sel + ((size_t)i * p.B + b) * HW + (size_t)v * W + u0;
+            if (u0 + 3 < W && ((W & 3) == 0)) *reinterpret_cast<unsigned*>(sp) = selw;
+            else {
+#pragma unroll
+                for (int k = 0; k < 4; k++) if (u0 + k < W) sp[k] = (unsigned char)((selw >> (8 * k)) & 0xff);
+            }
+        }
+        // smoothness: |inv[p]-inv[p+1]| * w_x * mask (the per-image 1/mean is applied in the finalise pass)
+        float smx = 0.f, smy = 0.f, isum = 0.f;
+        if (v < H) {
+            const float* ir = inv + (size_t)v * W;
+            float c4[5];
+#pragma unroll
+            for (int k = 0; k < 5; k++) c4[k] = (u0 + k < W) ? __ldg(ir + u0 + k) : 0.f;
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                float below = (v + 1 < H && u0 + k < W) ? __ldg(ir + W + u0 + k) : 0.f;
+                smx += wxm[k] * fabsf(c4[k] - c4[k + 1]);
+                smy += wym[k] * fabsf(c4[k] - below);
+                isum += valid[k] ? c4[k] : 0.f;
+            }
+        }
+        photo = warp_sum(photo); smx = warp_sum(smx); smy = warp_sum(smy); isum = warp_sum(isum);
+        if (lane == 0) { sRed[warp * 8 + 0] = photo; sRed[warp * 8 + 1] = smx; sRed[warp * 8 + 2] = smy; sRed[warp * 8 + 3] = isum; }
+        __syncthreads();   // sX free for the next scale; sRed complete
+        if (tid < 4) {
+            double acc = 0.0;
+#pragma unroll
+            for (int w = 0; w < NT / 32; w++) acc += (double)sRed[w * 8 + tid];
+            my_partials[tid * p.n + i] = acc;   // [photo | smx | smy | invsum][n]
+        }
+    }
+    // mask counts
+    cntN = warp_sum(cntN); cntX = warp_sum(cntX); cntY = warp_sum(cntY);
+    __syncthreads();
+    if (lane == 0) { sRed[warp * 8 + 4] = cntN; sRed[warp * 8 + 5] = cntX; sRed[warp * 8 + 6] = cntY; }
+    __syncthreads();
+    if (tid < 3) {
+        double acc = 0.0;
+#pragma unroll
+        for (int w = 0; w < NT / 32; w++) acc += (double)sRed[w * 8 + 4 + tid];
+        my_partials[4 * p.n + tid] = acc;
+    }
+}
+
+}  // namespace mgvs

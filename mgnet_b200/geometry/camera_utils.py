@@ -1,0 +1,53 @@
+"""Intrinsics helpers and ``view_synthesis`` with the reference's signatures
+(mgnet/geometry/camera_utils.py:10-54).  ``view_synthesis`` runs the sm_100a kernel
+``view_synthesis_kernel`` (forward only -- gradients flow through the fused loss, not through this
+stand-alone op); CPU tensors raise, there is no fallback."""
+import ctypes
+
+import torch
+
+from .. import _lib
+
+__all__ = ["construct_K", "scale_intrinsics", "view_synthesis"]
+
+
+def construct_K(fx, fy, cx, cy, dtype=torch.float, device=None):
+    return torch.tensor([[fx, 0, cx], [0, fy, cy], [0, 0, 1]], dtype=dtype, device=device)
+
+
+def scale_intrinsics(K, x_scale, y_scale):
+    """In-place rescale for a resized image; principal point follows the pixel-centre convention."""
+    K[..., 0, 0] *= x_scale
+    K[..., 1, 1] *= y_scale
+    K[..., 0, 2] = (K[..., 0, 2] + 0.5) * x_scale - 0.5
+    K[..., 1, 2] = (K[..., 1, 2] + 0.5) * y_scale - 0.5
+    return K
+
+
+def _stream(t):
+    return ctypes.c_void_p(torch.cuda.current_stream(t.device).cuda_stream)
+
+
+def view_synthesis(ref_image, depth, ref_cam, cam, mode="bilinear", padding_mode="zeros", return_coords=False):
+    assert depth.size(1) == 1
+    if mode != "bilinear" or padding_mode != "zeros":
+        raise NotImplementedError("view_synthesis kernel implements mode='bilinear', padding_mode='zeros' only")
+    if not (ref_image.is_cuda and depth.is_cuda):
+        raise RuntimeError("view_synthesis runs only on CUDA (sm_100a); there is no CPU fallback")
+    B, _, H, W = depth.shape
+    # target camera pose must be the identity as in the loss (cams[0], loss.py:127): the kernel lifts
+    # with K^-1 only and applies ref_cam.Tcw
+    ident = torch.eye(4, device=depth.device, dtype=torch.float32)
+    if not torch.equal(cam.Tcw.mat.float(), ident.expand_as(cam.Tcw.mat)):
+        raise NotImplementedError("view_synthesis kernel expects the target camera at the identity pose")
+    ref_image = ref_image.float().contiguous()
+    depth = depth.float().contiguous()
+    K = ref_cam.K.float().contiguous()
+    pose34 = ref_cam.Tcw.mat[:, :3, :4].float().contiguous()
+    warped = torch.empty_like(ref_image)
+    coords = torch.empty(B, H, W, 2, device=depth.device, dtype=torch.float32) if return_coords else None
+    with torch.cuda.device(depth.device):
+        _lib.check(_lib.lib().mgvs_view_synthesis(
+            B, H, W, ref_image.data_ptr(), depth.data_ptr(), K.data_ptr(), K.stride(0), K.stride(1), pose34.data_ptr(),
+            warped.data_ptr(), coords.data_ptr() if coords is not None else None, _stream(depth)), "mgvs_view_synthesis")
+    return (warped, coords) if return_coords else warped

@@ -1,0 +1,88 @@
+"""Drop-in replacement of ``mgnet.modeling.loss.MultiViewPhotometricLoss`` (reference loss.py:84-294).
+
+Same constructor arguments, same ``forward(predictions, targets)`` dictionary contract, same scales,
+automask / min-reprojection semantics, grid_sample padding ("zeros") and align_corners=True behaviour --
+but the arithmetic runs in two fused sm_100a kernels (mgnet_b200/csrc) reached through the C ABI in
+include/mgvs.h.  CUDA only: CPU tensors raise (no fallback).
+
+Plug-in seam (reference mg_net.py:744,757,772-779,792): pass an instance as ``loss=`` to
+``MGNetSelfSupervisedDepthHead`` or build it in ``from_config`` from ``cfg.MODEL.DEPTH_HEAD.*``.
+"""
+from __future__ import annotations
+
+import torch
+import torch.nn as nn
+
+from .ops import LossConfig, view_synthesis_loss
+
+__all__ = ["MultiViewPhotometricLoss"]
+
+
+class MultiViewPhotometricLoss(nn.Module):
+    def __init__(
+        self,
+        ssim_loss_weight,
+        photometric_loss_weight,
+        smoothing_loss_weight,
+        automask_loss,
+        photometric_reduce_op,
+        padding_mode,
+        process_group=None,
+        ddp_grad_scale=False,
+    ):
+        super().__init__()
+        self.n = None
+        self.ssim_loss_weight = ssim_loss_weight
+        self.photometric_loss_weight = photometric_loss_weight
+        self.smoothing_loss_weight = smoothing_loss_weight
+        self.automask_loss = automask_loss
+        self.photometric_reduce_op = photometric_reduce_op
+        self.padding_mode = padding_mode
+        self.process_group = process_group
+        self.ddp_grad_scale = ddp_grad_scale
+        self.last_selection = None   # uint8 [n,B,H,W] argmin of the most recent forward (new side output)
+        # same assertion as the reference (loss.py:106-109)
+        if self.automask_loss:
+            assert self.photometric_reduce_op == "min", \
+                "For automasking only the min photometric_reduce_op is supported."
+        # legal-but-unimplemented combinations fail loudly at construction time
+        if padding_mode != "zeros":
+            raise NotImplementedError("padding_mode=%r: the fused kernels implement 'zeros' only" % (padding_mode,))
+        if photometric_reduce_op not in ("min", "mean"):
+            raise NotImplementedError("Unknown photometric_reduce_op: {}".format(photometric_reduce_op))
+        if photometric_reduce_op == "mean":
+            raise NotImplementedError("photometric_reduce_op='mean' is not implemented by the fused kernels")
+        if not ssim_loss_weight > 0.0:
+            raise NotImplementedError("ssim_loss_weight == 0 (raw 3-channel L1 branch, loss.py:195-196) is not implemented")
+
+    def _config(self) -> LossConfig:
+        return LossConfig(
+            ssim_loss_weight=float(self.ssim_loss_weight),
+            photometric_loss_weight=float(self.photometric_loss_weight),
+            smoothing_loss_weight=float(self.smoothing_loss_weight),
+            automask_loss=bool(self.automask_loss),
+            photometric_reduce_op=self.photometric_reduce_op,
+            padding_mode=self.padding_mode,
+            process_group=self.process_group,
+            ddp_grad_scale=bool(self.ddp_grad_scale),
+        )
+
+    def forward(self, predictions, targets):
+        inv_depths = predictions["depth"]
+        pose_results = predictions["poses"]
+        self.n = len(inv_depths)
+        assert pose_results.shape[1] == 2, "Context and poses lists must be of same length"
+        # custom_fwd(cast_inputs=torch.float32) equivalent (mg_net.py:827): the op computes in fp32
+        with torch.autocast(device_type="cuda", enabled=False):
+            lp, ls, sel = view_synthesis_loss(
+                [d.float() for d in inv_depths],
+                pose_results.float(),
+                targets["image_orig"].float(),
+                targets["image_prev_orig"].float(),
+                targets["image_next_orig"].float(),
+                targets["camera_matrix"].float(),
+                targets["reprojection_mask"] if "reprojection_mask" in targets else None,
+                self._config(),
+            )
+        self.last_selection = sel
+        return {"loss_photometric": lp, "loss_smoothness": ls}

@@ -1,0 +1,177 @@
+"""torch.autograd glue around the C ABI (include/mgvs.h).  PyTorch is used here for device memory,
+streams and torch.distributed only; all arithmetic of the loss runs in libmgvs.so.
+"""
+from __future__ import annotations
+
+import ctypes
+from dataclasses import dataclass
+from typing import Optional
+
+import torch
+
+from . import _lib
+
+__all__ = ["LossConfig", "view_synthesis_loss", "launch_counter"]
+
+
+class _Counter:
+    """Counts kernel launches issued through the library (for bench.py's gpu_launches)."""
+
+    def __init__(self):
+        self.n = 0
+
+
+launch_counter = _Counter()
+FWD_LAUNCHES = 3   # prep_kernel, fwd_kernel, reduce_kernel
+FIN_LAUNCHES = 1   # finalize_kernel
+BWD_LAUNCHES = 2   # bwd_kernel, pose_reduce_kernel
+
+
+@dataclass(frozen=True)
+class LossConfig:
+    """The six constructor arguments of the reference loss (loss.py:87-109) plus sharding options."""
+    ssim_loss_weight: float = 0.85
+    photometric_loss_weight: float = 1.0
+    smoothing_loss_weight: float = 1e-3
+    automask_loss: bool = True
+    photometric_reduce_op: str = "min"
+    padding_mode: str = "zeros"
+    process_group: object = None      # torch.distributed group for the partial-sum all-reduce (None = local)
+    ddp_grad_scale: bool = False      # multiply local grads by world size so DDP's 1/G averaging yields the
+                                      # full-batch gradient; only with process_group
+
+
+def _require_cuda_f32(t: torch.Tensor, name: str, shape=None) -> torch.Tensor:
+    if not isinstance(t, torch.Tensor):
+        raise TypeError("%s must be a tensor" % name)
+    if not t.is_cuda:
+        raise RuntimeError("%s is on %s: the view-synthesis loss runs only on CUDA (sm_100a); there is no CPU fallback" % (name, t.device))
+    if t.dtype != torch.float32:
+        t = t.float()
+    if shape is not None and tuple(t.shape) != tuple(shape):
+        raise ValueError("%s has shape %s, expected %s" % (name, tuple(t.shape), tuple(shape)))
+    return t.contiguous()
+
+
+def _fill_problem(prob, cfg, tgt, prev, nxt, inv, camera, poses, mask, ws):
+    B, _, H, W = tgt.shape
+    prob.B, prob.H, prob.W, prob.n = B, H, W, len(inv)
+    prob.target = tgt.data_ptr()
+    prob.source[0] = prev.data_ptr()
+    prob.source[1] = nxt.data_ptr()
+    for i, d in enumerate(inv):
+        prob.inv_depth[i] = d.data_ptr()
+    prob.camera = camera.data_ptr()
+    prob.cam_batch_stride = camera.stride(0)
+    prob.cam_row_stride = camera.stride(1)
+    prob.poses = poses.data_ptr()
+    prob.mask = mask.data_ptr() if mask is not None else None
+    prob.ssim_weight = float(cfg.ssim_loss_weight)
+    prob.one_minus_ssim_weight = 1.0 - float(cfg.ssim_loss_weight)   # Python double, rounded to fp32 by ctypes
+    prob.photometric_weight = float(cfg.photometric_loss_weight)
+    prob.smoothing_weight = float(cfg.smoothing_loss_weight)
+    prob.automask = int(bool(cfg.automask_loss))
+    prob.reduce_op = 0
+    prob.padding_mode = 0
+    prob.workspace = ws.data_ptr()
+    prob.workspace_bytes = ws.numel()
+
+
+class _ViewSynthesisLoss(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, cfg: LossConfig, poses, camera, tgt, prev, nxt, mask, *inv):
+        L = _lib.lib()
+        if cfg.photometric_reduce_op != "min":
+            if cfg.photometric_reduce_op == "mean":
+                raise NotImplementedError("photometric_reduce_op='mean' is not implemented by the fused kernels")
+            raise NotImplementedError("Unknown photometric_reduce_op: {}".format(cfg.photometric_reduce_op))
+        if cfg.padding_mode != "zeros":
+            raise NotImplementedError("padding_mode=%r is not implemented by the fused kernels (only 'zeros')" % (cfg.padding_mode,))
+        n = len(inv)
+        if n < 1 or n > _lib.MAX_SCALES:
+            raise ValueError("need 1..%d inverse-depth maps, got %d" % (_lib.MAX_SCALES, n))
+        tgt = _require_cuda_f32(tgt, "image_orig")
+        B, C, H, W = tgt.shape
+        if C != 3:
+            raise ValueError("image_orig must be [B,3,H,W]")
+        prev = _require_cuda_f32(prev, "image_prev_orig", (B, 3, H, W))
+        nxt = _require_cuda_f32(nxt, "image_next_orig", (B, 3, H, W))
+        inv = [_require_cuda_f32(d, "depth[%d]" % i, (B, 1, H, W)) for i, d in enumerate(inv)]
+        poses = _require_cuda_f32(poses, "poses", (B, 2, 6))
+        if camera.dim() != 3 or camera.shape[0] != B or camera.shape[1] < 3 or camera.shape[2] < 3:
+            raise ValueError("camera_matrix must be [B,>=3,>=3]")
+        camera = _require_cuda_f32(camera, "camera_matrix")
+        if mask is not None:
+            if not mask.is_cuda:
+                raise RuntimeError("reprojection_mask must be on CUDA")
+            if tuple(mask.shape) != (B, 1, H, W):
+                raise ValueError("reprojection_mask must be [B,1,H,W]")
+            if mask.dtype != torch.bool:
+                mask = mask != 0
+            mask = mask.contiguous()
+        dev = tgt.device
+        with torch.cuda.device(dev):
+            ws = torch.empty(int(L.mgvs_workspace_bytes(B, H, W, n)), dtype=torch.uint8, device=dev)
+            sel = torch.empty((n, B, H, W), dtype=torch.uint8, device=dev)
+            sums = torch.empty(3 * n + 3, dtype=torch.float64, device=dev)
+            losses = torch.empty(2, dtype=torch.float32, device=dev)
+            prob = _lib.MgvsProblem()
+            _fill_problem(prob, cfg, tgt, prev, nxt, inv, camera, poses, mask, ws)
+            stream = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+            _lib.check(L.mgvs_forward(ctypes.byref(prob), sel.data_ptr(), sums.data_ptr(), stream), "mgvs_forward")
+            launch_counter.n += FWD_LAUNCHES
+            world = 1
+            if cfg.process_group is not None:
+                import torch.distributed as dist
+                dist.all_reduce(sums, op=dist.ReduceOp.SUM, group=cfg.process_group)
+                world = dist.get_world_size(cfg.process_group)
+            _lib.check(L.mgvs_finalize(ctypes.byref(prob), sums.data_ptr(), losses.data_ptr(), stream), "mgvs_finalize")
+            launch_counter.n += FIN_LAUNCHES
+        ctx.cfg = cfg
+        ctx.n = n
+        ctx.has_mask = mask is not None
+        ctx.grad_scale = float(world) if (cfg.ddp_grad_scale and cfg.process_group is not None) else 1.0
+        saved = [poses, camera, tgt, prev, nxt, sel, sums, ws] + ([mask] if mask is not None else []) + list(inv)
+        ctx.save_for_backward(*saved)
+        ctx.mark_non_differentiable(sel)
+        lp, ls = losses.unbind(0)
+        return lp, ls, sel
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, g_photo, g_smooth, _g_sel):
+        L = _lib.lib()
+        saved = ctx.saved_tensors
+        poses, camera, tgt, prev, nxt, sel, sums, ws = saved[:8]
+        k = 8
+        mask = None
+        if ctx.has_mask:
+            mask = saved[8]
+            k = 9
+        inv = list(saved[k:])
+        dev = tgt.device
+        with torch.cuda.device(dev):
+            g = torch.zeros(2, dtype=torch.float32, device=dev)
+            if g_photo is not None:
+                g[0] = g_photo
+            if g_smooth is not None:
+                g[1] = g_smooth
+            if ctx.grad_scale != 1.0:
+                g = g * ctx.grad_scale
+            grads = [torch.empty_like(d) for d in inv]
+            gp = torch.empty_like(poses)
+            prob = _lib.MgvsProblem()
+            _fill_problem(prob, ctx.cfg, tgt, prev, nxt, inv, camera, poses, mask, ws)
+            arr = (ctypes.c_void_p * len(grads))(*[x.data_ptr() for x in grads])
+            stream = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+            _lib.check(L.mgvs_backward(ctypes.byref(prob), sel.data_ptr(), sums.data_ptr(), g.data_ptr(), arr,
+                                       gp.data_ptr(), stream), "mgvs_backward")
+            launch_counter.n += BWD_LAUNCHES
+        return (None, gp, None, None, None, None, None) + tuple(grads)
+
+
+def view_synthesis_loss(inv_depths, poses, image, image_prev, image_next, camera_matrix,
+                        reprojection_mask: Optional[torch.Tensor] = None, cfg: LossConfig = LossConfig()):
+    """Functional form.  Returns (loss_photometric, loss_smoothness, selection uint8 [n,B,H,W])."""
+    return _ViewSynthesisLoss.apply(cfg, poses, camera_matrix, image, image_prev, image_next, reprojection_mask,
+                                    *inv_depths)

@@ -1,0 +1,162 @@
+"""GPU parity tests (run on the B200 box with -m gpu).  Everything goes through the C ABI
+(mgnet_b200/_lib.py -> libmgvs.so); the checker is the golden fixtures made by the reference and the
+CPU oracle (oracle/), never the thing under test.
+
+Bars (BASELINE.json north_star): losses <= 1e-5 relative, depth/pose gradients <= 1e-4 relative
+(L2 norm and max norm), selection mask bit-exact.
+"""
+import ctypes
+
+import numpy as np
+import pytest
+import torch
+
+from helpers import GRAD_RTOL, LOSS_RTOL, golden_names, l2rel, load_golden, maxrel, relerr
+
+pytestmark = pytest.mark.gpu
+
+OR_KEYS = ("ssim_loss_weight", "photometric_loss_weight", "smoothing_loss_weight", "automask_loss")
+
+
+def _dev():
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+    return torch.device("cuda:0")
+
+
+def _to_dev(pred, tgt, dev, grad=True):
+    p = {"depth": [d.to(dev).requires_grad_(grad) for d in pred["depth"]], "poses": pred["poses"].to(dev).requires_grad_(grad)}
+    t = {k: v.to(dev) for k, v in tgt.items()}
+    return p, t
+
+
+def _run_cuda(pred, tgt, hp, dev, g=(1.0, 1.0)):
+    from mgnet_b200 import MultiViewPhotometricLoss
+    mod = MultiViewPhotometricLoss(**hp)
+    p, t = _to_dev(pred, tgt, dev)
+    out = mod(p, t)
+    (g[0] * out["loss_photometric"] + g[1] * out["loss_smoothness"]).backward()
+    torch.cuda.synchronize()
+    return {
+        "loss_photometric": out["loss_photometric"].item(),
+        "loss_smoothness": out["loss_smoothness"].item(),
+        "sel": mod.last_selection.cpu().numpy(),
+        "grad_depth": [d.grad.cpu().numpy() for d in p["depth"]],
+        "grad_poses": p["poses"].grad.cpu().numpy(),
+    }
+
+
+def test_library_loaded_is_in_tree():
+    _dev()
+    from mgnet_b200 import _lib
+    L = _lib.lib()
+    assert L.mgvs_abi_version() == 1
+    assert _lib.LIB_PATH.endswith("mgnet_b200/libmgvs.so")
+
+
+@pytest.mark.parametrize("name", golden_names())
+def test_golden_forward(name):
+    dev = _dev()
+    pred, tgt, hp, ref = load_golden(name)
+    r = _run_cuda(pred, tgt, hp, dev)
+    assert relerr(r["loss_photometric"], ref["loss_photometric"]) <= LOSS_RTOL
+    assert relerr(r["loss_smoothness"], ref["loss_smoothness"]) <= LOSS_RTOL
+    for i in range(len(pred["depth"])):
+        mism = int((r["sel"][i] != ref["sel_%d" % i][:, 0]).sum())
+        assert mism == 0, "scale %d: %d selection mismatches vs the reference" % (i, mism)
+
+
+@pytest.mark.parametrize("name", golden_names())
+def test_golden_backward(name):
+    dev = _dev()
+    pred, tgt, hp, ref = load_golden(name)
+    r = _run_cuda(pred, tgt, hp, dev)
+    for i in range(len(pred["depth"])):
+        assert l2rel(r["grad_depth"][i], ref["grad_depth_%d" % i]) <= GRAD_RTOL
+        assert maxrel(r["grad_depth"][i], ref["grad_depth_%d" % i]) <= GRAD_RTOL
+    assert l2rel(r["grad_poses"], ref["grad_poses"]) <= GRAD_RTOL
+    assert maxrel(r["grad_poses"], ref["grad_poses"]) <= GRAD_RTOL
+
+
+@pytest.mark.parametrize("shape", [(2, 192, 640, 3, 0.2, False), (1, 96, 320, 4, 0.0, True), (3, 50, 70, 2, 0.2, False)])
+def test_against_oracle(shape):
+    """Sizes the oracle finishes in seconds, incl. H/W that are not multiples of the 64x16 tile."""
+    dev = _dev()
+    from mgnet_b200.synthetic import make_inputs
+    from oracle.oracle import Oracle
+    B, H, W, n, noise, shift = shape
+    pred, tgt = make_inputs(B, H, W, n, seed=11, noise=noise, shift_sources=shift)
+    hp = dict(ssim_loss_weight=0.85, photometric_loss_weight=1.0, smoothing_loss_weight=1e-3, automask_loss=True,
+              photometric_reduce_op="min", padding_mode="zeros")
+    o = Oracle(pred, tgt, **{k: hp[k] for k in OR_KEYS})
+    f = o.forward()
+    g = o.backward(1.0, 1.0)
+    r = _run_cuda(pred, tgt, hp, dev)
+    assert relerr(r["loss_photometric"], f["loss_photometric"]) <= LOSS_RTOL
+    assert relerr(r["loss_smoothness"], f["loss_smoothness"]) <= LOSS_RTOL
+    assert int((r["sel"] != f["sel"]).sum()) == 0
+    for i in range(n):
+        assert l2rel(r["grad_depth"][i], g["grad_depth"][i]) <= GRAD_RTOL
+        assert maxrel(r["grad_depth"][i], g["grad_depth"][i]) <= GRAD_RTOL
+    assert l2rel(r["grad_poses"], g["grad_poses"]) <= GRAD_RTOL
+
+
+def test_backward_deterministic_and_linear():
+    dev = _dev()
+    pred, tgt, hp, ref = load_golden("grad_smooth_shift")
+    a = _run_cuda(pred, tgt, hp, dev)
+    b = _run_cuda(pred, tgt, hp, dev)
+    for x, y in zip(a["grad_depth"], b["grad_depth"]):
+        assert np.array_equal(x, y)
+    assert np.array_equal(a["grad_poses"], b["grad_poses"])
+    c = _run_cuda(pred, tgt, hp, dev, g=(2.0, 3.0))
+    p10 = _run_cuda(pred, tgt, hp, dev, g=(1.0, 0.0))
+    p01 = _run_cuda(pred, tgt, hp, dev, g=(0.0, 1.0))
+    for i in range(len(pred["depth"])):
+        assert l2rel(c["grad_depth"][i], 2.0 * p10["grad_depth"][i].astype(np.float64) + 3.0 * p01["grad_depth"][i]) <= 1e-5
+    assert np.abs(p01["grad_poses"]).max() == 0.0
+
+
+def test_exact_division_matches_ieee():
+    dev = _dev()
+    from mgnet_b200 import _lib
+    L = _lib.lib()
+    g = torch.Generator(device="cpu").manual_seed(5)
+    n = 1 << 22
+    cases = []
+    a = (torch.rand(n, generator=g) * 4 - 2) * torch.exp(torch.randn(n, generator=g) * 6)
+    b = (torch.rand(n, generator=g) + 1e-3) * torch.exp(torch.randn(n, generator=g) * 6)
+    cases.append((a, b))
+    for d in (63.0, 95.0, 191.0, 639.0, 1023.0, 2047.0, 511.0, 71.0, 39.0):
+        cases.append(((torch.rand(n, generator=g) * 2 - 1) * 4000.0, torch.full((n,), d)))
+    for a, b in cases:
+        a, b = a.float().to(dev), b.float().to(dev)
+        out = torch.empty_like(a)
+        _lib.check(L.mgvs_test_div(a.data_ptr(), b.data_ptr(), out.data_ptr(), a.numel(),
+                                   ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)))
+        torch.cuda.synchronize()
+        ref = (a.double() / b.double()).float()      # correctly rounded (double rounding is safe: 53 >= 2*24+2)
+        assert int((out != ref).sum()) == 0
+
+
+def test_view_synthesis_matches_reference_intermediates():
+    dev = _dev()
+    from mgnet_b200.geometry import Camera, Pose, inv2depth, view_synthesis
+    pred, tgt, hp, ref = load_golden("kitti_small_mask")
+    K = tgt["camera_matrix"][:, :3, :3].to(dev)
+    for s, key in enumerate(("image_prev_orig", "image_next_orig")):
+        pose = Pose.from_vec(pred["poses"][:, s].to(dev), "euler")
+        # the pose matrix itself must match the reference's bit for bit (trig boundary: snapped angles)
+        depth = inv2depth(pred["depth"][0].to(dev))
+        pose_ref = Pose(torch.from_numpy(ref["pose_mat"][:, s]).to(dev))
+        warped, coords = view_synthesis(tgt[key].to(dev), depth, Camera(K, Tcw=pose_ref), Camera(K).to(dev), return_coords=True)
+        assert np.array_equal(coords.cpu().numpy(), ref["coords_0_%d" % s])
+        assert np.array_equal(warped.cpu().numpy(), ref["warped_0_%d" % s])
+
+
+def test_cpu_tensors_raise():
+    _dev()
+    from mgnet_b200 import MultiViewPhotometricLoss
+    pred, tgt, hp, ref = load_golden("nomask_n1")
+    with pytest.raises(RuntimeError):
+        MultiViewPhotometricLoss(**hp)(pred, tgt)
