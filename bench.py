@@ -1,0 +1,383 @@
+#!/usr/bin/env python
+"""bench.py -- view-synthesis loss fwd+bwd throughput (Gpixel/s) on N B200s of one node.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c2|c3|c4|c1] [--impl reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+        bench.py --gpus N --steps K --warmup W
+
+One "step" = one forward + one backward of the loss over one batch of synthetic inputs (pixels counted
+as B*H*W target pixels).  Prints ONE JSON line on rank 0:
+
+  value      whole-job Gpixel/s with inputs resident in HBM (device-timed, max over ranks)
+  e2e        the same metric through the public module with HOST (pinned) inputs: H2D copies of every
+             input and a D2H read of the two losses inside the timed region
+  roofline   dominant kernel (bwd_kernel): algorithmic bytes per launch / CUDA-event duration, against the
+             measured HBM peak in MEASURED_PEAKS.json
+  cpu_baseline  the ATen-level port of the reference (oracle/torch_port.py) on this box's host cores,
+             bounded sample (N=1, rank 0 only)
+
+--impl reference times that CPU port alone (the Python reference cannot travel to the GPU box; the port is
+bit-identical to it, tests/test_torch_port.py) and prints the same line with "impl": "reference".
+Multi-GPU: the batch shards by image; the only exchange is one NCCL all-reduce of 3n+3 doubles (weak scaling).
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+WORKLOADS = {
+    # name: (description, B per GPU, H, W, n)
+    "c1": ("KITTI Eigen-Zhou self-supervised loss, batch 1, 192x640, 2 source frames, 3 scales", 1, 192, 640, 3),
+    "c2": ("KITTI Eigen-Zhou loss fwd+bwd, batch 16, 192x640, 2 source frames, 3 scales, automask on", 16, 192, 640, 3),
+    "c3": ("Cityscapes-VideoSequence loss fwd+bwd, batch 8, 512x1024, 4 scales at full res", 8, 512, 1024, 4),
+    "c4": ("Cityscapes full-res 1024x2048 loss fwd+bwd, batch 8 per GPU (64 over 8 GPUs), 3 scales", 8, 1024, 2048, 3),
+}
+HP = dict(ssim_loss_weight=0.85, photometric_loss_weight=1.0, smoothing_loss_weight=1e-3, automask_loss=True,
+          photometric_reduce_op="min", padding_mode="zeros")
+L2_BYTES = 126 * 1024 * 1024
+
+
+def bytes_per_pixel(n, S=2, mask=True):
+    m = 1 if mask else 0
+    fwd = 12 + 12 * S + 4 * n + m
+    return {"fwd": fwd, "bwd": fwd + 4 * n, "fwd_bwd": 2 * fwd + 4 * n}
+
+
+def measured_peak():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.proc = None
+        self.path = None
+
+    def start(self):
+        try:
+            fd, self.path = tempfile.mkstemp(suffix=".csv")
+            os.close(fd)
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "200"],
+                stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if self.proc is None:
+            return out
+        try:
+            self.proc.terminate()
+            self.proc.wait(timeout=5)
+        except Exception:
+            pass
+        try:
+            rows = [r.strip().split(",") for r in open(self.path) if r.strip()]
+            sm = [float(r[0]) for r in rows if len(r) >= 6]
+            if sm:
+                out["sm_mhz"] = statistics.median(sm)
+                out["sm_max_mhz"] = float(rows[0][1])
+                names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+                for k, nm in enumerate(names):
+                    if any(r[2 + k].strip().lower().startswith("active") for r in rows if len(r) >= 6):
+                        out["reasons"].append(nm)
+                out["samples"] = len(sm)
+        except Exception:
+            pass
+        finally:
+            try:
+                os.unlink(self.path)
+            except Exception:
+                pass
+        return out
+
+
+def cpu_reference_run(desc, B_sample, H, W, n, steps, warmup, seed=0):
+    """Times the ATen-level port of the reference (fwd+bwd) on all host cores.  Returns (Gpx/s, ms, info)."""
+    from mgnet_b200.synthetic import make_inputs
+    from oracle.torch_port import reference_loss
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    pred, tgt = make_inputs(B_sample, H, W, n, seed=seed)
+    inv = [d.clone().requires_grad_(True) for d in pred["depth"]]
+    poses = pred["poses"].clone().requires_grad_(True)
+    kw = {k: HP[k] for k in ("ssim_loss_weight", "photometric_loss_weight", "smoothing_loss_weight", "automask_loss")}
+
+    def step():
+        for t in inv + [poses]:
+            t.grad = None
+        out = reference_loss({"depth": inv, "poses": poses}, tgt, **kw)
+        (out["loss_photometric"] + out["loss_smoothness"]).backward()
+        return float(out["loss_photometric"].detach())
+
+    for _ in range(warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    dt = (time.perf_counter() - t0) / max(steps, 1)
+    px = B_sample * H * W
+    sample = "%d of the workload's images per step (B=%d, %dx%d, n=%d), %d steps after %d warm-up, torch %s, %d threads" % (
+        B_sample, B_sample, H, W, n, steps, warmup, torch.__version__, torch.get_num_threads())
+    return px / dt / 1e9, dt * 1e3, {"cores": cores, "kind": "port", "sample": sample}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    desc, B, H, W, n = WORKLOADS[args.workload]
+    bpp = bytes_per_pixel(n)
+
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        Bs = min(B, 4)
+        val, ms, info = cpu_reference_run(desc, Bs, H, W, n, max(args.steps, 1), args.warmup)
+        line = {
+            "impl": "reference", "metric": "view-synth loss fwd+bwd Gpixel/s", "value": val, "unit": "Gpixel/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": desc, "B_per_step": Bs, "H": H, "W": W, "scales": n, "sources": 2},
+            "cpu_baseline": dict(info, value=val, unit="Gpixel/s"),
+            "e2e": {"value": val, "unit": "Gpixel/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0,
+        }
+        print(json.dumps(line))
+        return 0
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the B200 arm has no CPU fallback (use --impl reference for the CPU port)")
+    dev = torch.device("cuda", local_rank)
+    torch.cuda.set_device(dev)
+    import torch.distributed as dist
+    group = None
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+        group = dist.group.WORLD
+
+    from mgnet_b200 import MultiViewPhotometricLoss, _lib, ops
+    from mgnet_b200.synthetic import make_inputs
+    L = _lib.lib()
+    mod = MultiViewPhotometricLoss(process_group=group, ddp_grad_scale=False, **HP)
+
+    # rotating input sets so that no step finds its inputs in L2 (inputs of one set are < L2 for c1/c2)
+    in_bytes = B * H * W * (36 + 4 * n + 1)
+    nsets = max(2, min(6, -(-3 * L2_BYTES // in_bytes))) if in_bytes < 2 * L2_BYTES else 2
+    sets_host, sets_dev = [], []
+    for k in range(nsets):
+        pred, tgt = make_inputs(B, H, W, n, seed=100 + 10 * rank + k)
+        sets_host.append((pred, tgt))
+        p = {"depth": [d.to(dev).requires_grad_(True) for d in pred["depth"]], "poses": pred["poses"].to(dev).requires_grad_(True)}
+        t = {kk: v.to(dev) for kk, v in tgt.items()}
+        sets_dev.append((p, t))
+
+    def step_dev(k):
+        p, t = sets_dev[k % nsets]
+        for x in p["depth"] + [p["poses"]]:
+            x.grad = None
+        out = mod(p, t)
+        (out["loss_photometric"] + out["loss_smoothness"]).backward()
+        return out
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for k in range(args.warmup):
+        step_dev(k)
+    barrier()
+    try:
+        gpu_id = "GPU-" + str(torch.cuda.get_device_properties(dev).uuid)
+    except Exception:
+        gpu_id = str(local_rank)
+    sampler = ClockSampler(gpu_id)
+    if rank == 0:
+        sampler.start()
+    ops.launch_counter.n = 0
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for k in range(args.steps):
+        step_dev(k)
+    e1.record()
+    barrier()
+    launches = ops.launch_counter.n
+    ms_total = e0.elapsed_time(e1)
+    tt = torch.tensor([ms_total], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    ms_step = float(tt.item()) / args.steps
+    px_step = B * H * W * world
+    value = px_step / (ms_step * 1e-3) / 1e9
+
+    # ---- per-kernel timing through the C ABI (dominant kernel roofline) ----
+    p, t = sets_dev[0]
+    from mgnet_b200.ops import LossConfig, _fill_problem
+    cfg = LossConfig(**HP)
+    ws = torch.empty(int(L.mgvs_workspace_bytes(B, H, W, n)), dtype=torch.uint8, device=dev)
+    sel = torch.empty((n, B, H, W), dtype=torch.uint8, device=dev)
+    sums = torch.empty(3 * n + 3, dtype=torch.float64, device=dev)
+    losses = torch.empty(2, dtype=torch.float32, device=dev)
+    g = torch.ones(2, dtype=torch.float32, device=dev)
+    grads = [torch.empty_like(d) for d in p["depth"]]
+    gp = torch.empty_like(p["poses"])
+    arr = (ctypes.c_void_p * n)(*[x.data_ptr() for x in grads])
+    stream = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+    kt = {"fwd": [], "bwd": []}
+    for k in range(args.warmup + min(args.steps, 20)):
+        pk, tk = sets_dev[k % nsets]
+        prob = _lib.MgvsProblem()
+        inv_k = [d.detach() for d in pk["depth"]]
+        _fill_problem(prob, cfg, tk["image_orig"], tk["image_prev_orig"], tk["image_next_orig"], inv_k,
+                      tk["camera_matrix"], pk["poses"].detach(), tk.get("reprojection_mask"), ws)
+        a, b_, c = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+        a.record()
+        _lib.check(L.mgvs_forward(ctypes.byref(prob), sel.data_ptr(), sums.data_ptr(), stream))
+        _lib.check(L.mgvs_finalize(ctypes.byref(prob), sums.data_ptr(), losses.data_ptr(), stream))
+        b_.record()
+        _lib.check(L.mgvs_backward(ctypes.byref(prob), sel.data_ptr(), sums.data_ptr(), g.data_ptr(), arr, gp.data_ptr(), stream))
+        c.record()
+        torch.cuda.synchronize()
+        if k >= args.warmup:
+            kt["fwd"].append(a.elapsed_time(b_))
+            kt["bwd"].append(b_.elapsed_time(c))
+    fwd_ms, bwd_ms = statistics.mean(kt["fwd"]), statistics.mean(kt["bwd"])
+    peak, peak_src = measured_peak()
+    px_gpu = B * H * W
+    dominant = "bwd" if bwd_ms >= fwd_ms else "fwd"
+    dom_ms = bwd_ms if dominant == "bwd" else fwd_ms
+    achieved = px_gpu * bpp[dominant] / (dom_ms * 1e-3) / 1e9
+    traffic = None
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            traffic = json.load(f).get(args.workload, {}).get(dominant + "_kernel_dram_bytes_per_launch")
+    except Exception:
+        pass
+    roofline = {"bound": "hbm", "kernel": dominant + "_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": px_gpu * bpp[dominant], "launch_ms": dom_ms,
+                "fwd_call_ms": fwd_ms, "bwd_call_ms": bwd_ms,
+                "fwd_bwd_frac": px_gpu * bpp["fwd_bwd"] / ((fwd_ms + bwd_ms) * 1e-3) / 1e9 / peak}
+
+    # ---- end to end: pinned host inputs -> H2D -> module fwd+bwd -> D2H of the two losses ----
+    e2e = None
+    if not args.no_e2e:
+        def pin(x):
+            return x.pin_memory()
+        host = []
+        for pred, tgt in sets_host:
+            host.append(({"depth": [pin(d) for d in pred["depth"]], "poses": pin(pred["poses"])}, {kk: pin(v) for kk, v in tgt.items()}))
+        h2d = sum(d.numel() * d.element_size() for d in host[0][0]["depth"]) + host[0][0]["poses"].numel() * 4 + \
+            sum(v.numel() * v.element_size() for v in host[0][1].values())
+        copy_stream = torch.cuda.Stream(dev)
+        out_host = torch.empty(2, dtype=torch.float32).pin_memory()
+        slots = [None, None]
+
+        def upload(k):
+            hp_, ht_ = host[k % nsets]
+            with torch.cuda.stream(copy_stream):
+                pd = {"depth": [d.to(dev, non_blocking=True) for d in hp_["depth"]], "poses": hp_["poses"].to(dev, non_blocking=True)}
+                td = {kk: v.to(dev, non_blocking=True) for kk, v in ht_.items()}
+                ev = torch.cuda.Event()
+                ev.record(copy_stream)
+            slots[k % 2] = (pd, td, ev)
+
+        def e2e_step(k, last):
+            pd, td, ev = slots[k % 2]
+            torch.cuda.current_stream(dev).wait_event(ev)
+            if not last:
+                upload(k + 1)      # prefetch the next step's inputs while this step computes
+            for x in pd["depth"] + [pd["poses"]]:
+                x.requires_grad_(True)
+            out = mod(pd, td)
+            (out["loss_photometric"] + out["loss_smoothness"]).backward()
+            out_host.copy_(torch.stack([out["loss_photometric"].detach(), out["loss_smoothness"].detach()]), non_blocking=True)
+            for tns in pd["depth"] + [pd["poses"]] + list(td.values()):
+                tns.record_stream(torch.cuda.current_stream(dev))
+
+        upload(0)
+        for k in range(args.warmup):
+            e2e_step(k, False)
+        barrier()
+        t0 = time.perf_counter()
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s0.record()
+        base = args.warmup
+        for k in range(args.steps):
+            e2e_step(base + k, k == args.steps - 1)
+        s1.record()
+        barrier()
+        wall_ms = (time.perf_counter() - t0) * 1e3
+        ms_e = max(s0.elapsed_time(s1), 0.0)
+        te = torch.tensor([ms_e], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        ms_e = float(te.item()) / args.steps
+        e2e = {"value": px_step / (ms_e * 1e-3) / 1e9, "unit": "Gpixel/s", "h2d_bytes_per_step": int(h2d),
+               "d2h_bytes_per_step": 8, "ms_per_step": ms_e, "wall_ms_per_step": wall_ms / args.steps,
+               "note": "pinned host inputs, H2D of step k+1 overlapped with compute of step k on a copy stream"}
+
+    clocks = sampler.stop() if rank == 0 else None
+
+    cpu_base = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        Bs = min(B, 4)
+        v, ms, info = cpu_reference_run(desc, Bs, H, W, n, 3, 1)
+        cpu_base = dict(info, value=v, unit="Gpixel/s", ms_per_sample_step=ms)
+
+    if rank == 0:
+        line = {
+            "metric": "view-synth loss fwd+bwd Gpixel/s", "value": value, "unit": "Gpixel/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": desc, "B_per_gpu": B, "H": H, "W": W, "scales": n, "sources": 2, "mask": True,
+                       "l2": "rotating %d input sets (%.0f MB) so inputs are never L2-resident" % (nsets, nsets * in_bytes / 1e6),
+                       "parallelism": "batch-sharded x%d, one NCCL all-reduce of %d doubles per step" % (world, 3 * n + 3) if world > 1 else "single GPU",
+                       "bytes_per_pixel_fwd_bwd": bpp["fwd_bwd"]},
+            "roofline": roofline, "cpu_baseline": cpu_base, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
+            "hbm_frac_fwd_bwd": value / world * bpp["fwd_bwd"] / peak,
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

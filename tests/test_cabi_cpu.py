@@ -1,0 +1,74 @@
+"""CPU: the C-ABI library builds for sm_100a without a GPU, loads, and exports every symbol that
+include/mgvs.h declares (no compute calls here); host-side argument validation."""
+import ctypes
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_symbols():
+    src = open(os.path.join(ROOT, "include", "mgvs.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(mgvs_[a-z_0-9]+)\s*\(", src)))
+
+
+def test_header_symbols_exported():
+    from mgnet_b200 import _lib
+    path = _lib.build()
+    L = ctypes.CDLL(path)
+    decl = _declared_symbols()
+    assert len(decl) >= 10
+    for sym in decl:
+        assert hasattr(L, sym), "include/mgvs.h declares %s but libmgvs.so does not export it" % sym
+    assert sorted(_lib.EXPORTED_SYMBOLS) == decl
+
+
+def test_host_side_queries():
+    from mgnet_b200 import _lib
+    L = _lib.lib()
+    assert L.mgvs_abi_version() == 1
+    assert L.mgvs_num_sums(3) == 12
+    ws = L.mgvs_workspace_bytes(16, 192, 640, 3)
+    assert ws > 0 and ws % 256 == 0
+    assert L.mgvs_workspace_bytes(0, 192, 640, 3) == 0
+    assert L.mgvs_workspace_bytes(1, 192, 640, 9) == 0
+
+
+def test_struct_layout_matches_header():
+    """ctypes mirror must have the size the C compiler gives the struct (checked by compiling a probe)."""
+    import subprocess
+    import tempfile
+    from mgnet_b200 import _lib
+    with tempfile.TemporaryDirectory() as d:
+        src = os.path.join(d, "p.c")
+        open(src, "w").write('#include <stdio.h>\n#include "mgvs.h"\nint main(){printf("%zu\\n", sizeof(MgvsProblem));return 0;}\n')
+        exe = os.path.join(d, "p")
+        subprocess.run(["/usr/bin/gcc", "-I", os.path.join(ROOT, "include"), "-o", exe, src], check=True)
+        size = int(subprocess.run([exe], capture_output=True, text=True, check=True).stdout)
+    assert ctypes.sizeof(_lib.MgvsProblem) == size
+
+
+def test_module_rejects_unsupported_configs_loudly():
+    from mgnet_b200 import MultiViewPhotometricLoss
+    with pytest.raises(NotImplementedError):
+        MultiViewPhotometricLoss(0.85, 1.0, 1e-3, True, "min", "border")
+    with pytest.raises(AssertionError):
+        MultiViewPhotometricLoss(0.85, 1.0, 1e-3, True, "mean", "zeros")
+    with pytest.raises(NotImplementedError):
+        MultiViewPhotometricLoss(0.85, 1.0, 1e-3, False, "mean", "zeros")
+    with pytest.raises(NotImplementedError):
+        MultiViewPhotometricLoss(0.85, 1.0, 1e-3, False, "median", "zeros")
+    with pytest.raises(NotImplementedError):
+        MultiViewPhotometricLoss(0.0, 1.0, 1e-3, True, "min", "zeros")
+
+
+def test_cpu_tensors_fail_loudly_no_fallback():
+    import torch
+    from mgnet_b200 import MultiViewPhotometricLoss
+    from mgnet_b200.synthetic import make_inputs
+    pred, tgt = make_inputs(1, 32, 64, 1, seed=0)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        MultiViewPhotometricLoss(0.85, 1.0, 1e-3, True, "min", "zeros")(pred, tgt)
