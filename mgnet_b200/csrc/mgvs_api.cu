@@ -1,5 +1,6 @@
 // mgvs_api.cu -- small kernels (camera table, fixed-order reductions, finalise, pose chain) and the
 // extern "C" entry points declared in include/mgvs.h.  Built for sm_100a only.
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdint.h>
@@ -17,6 +18,50 @@ static int fail(int code, const char* msg)
 {
     snprintf(g_err, sizeof(g_err), "%s", msg);
     return code;
+}
+
+// ---------------------------------------------------------------------------------------------
+// TMA descriptors.  cuTensorMapEncodeTiled is resolved through the runtime (no link against libcuda, so
+// the library still loads on a machine without a driver).  A [planes, H, W] fp32 tensor is described as a
+// 3-D map with box {72, rows, depth}; zero fill for out-of-bounds elements.
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn encode_fn()
+{
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* ptr = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = (EncodeTiledFn)ptr;
+    }
+    return fn;
+}
+static bool make_map(TmaDesc* out, const float* base, int planes, int H, int W, int box_rows, int box_depth)
+{
+    EncodeTiledFn fn = encode_fn();
+    if (!fn) return false;
+    static_assert(sizeof(CUtensorMap) == sizeof(TmaDesc), "CUtensorMap is 128 bytes");
+    cuuint64_t dims[3] = {(cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)planes};
+    cuuint64_t strides[2] = {(cuuint64_t)W * 4, (cuuint64_t)W * H * 4};
+    cuuint32_t box[3] = {(cuuint32_t)PITCH, (cuuint32_t)box_rows, (cuuint32_t)box_depth};
+    cuuint32_t es[3] = {1, 1, 1};
+    CUresult r = fn(reinterpret_cast<CUtensorMap*>(out), CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void*)base, dims, strides, box, es,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS;
+}
+// TMA needs 16-byte aligned bases and row strides (W % 4 == 0); otherwise the kernels use their manual loaders.
+static bool tma_eligible(const MgvsProblem* p)
+{
+    if (p->W % 4 != 0) return false;
+    auto al = [](const void* q) { return ((uintptr_t)q & 15) == 0; };
+    if (!al(p->target) || !al(p->source[0]) || !al(p->source[1])) return false;
+    for (int i = 0; i < p->n; i++)
+        if (!al(p->inv_depth[i])) return false;
+    return encode_fn() != nullptr;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -367,8 +412,22 @@ int mgvs_forward(const MgvsProblem* p, unsigned char* sel, double* sums, void* c
     fp.partials = (double*)(ws + L.partials);
     fp.alpha = p->ssim_weight; fp.oma = p->one_minus_ssim_weight;
     fp.tiles_x = L.tiles_x; fp.tiles_y = L.tiles_y;
-    cudaFuncSetAttribute(fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FWD_SMEM_BYTES);
-    fwd_kernel<<<L.tiles, NT, FWD_SMEM_BYTES, st>>>(fp);
+    FwdMaps maps;
+    bool use_tma = tma_eligible(p);
+    if (use_tma) {
+        use_tma = make_map(&maps.tgt, p->target, 3 * p->B, p->H, p->W, FWD_ROWS, 3) &&
+                  make_map(&maps.src[0], p->source[0], 3 * p->B, p->H, p->W, FWD_ROWS, 3) &&
+                  make_map(&maps.src[1], p->source[1], 3 * p->B, p->H, p->W, FWD_ROWS, 3);
+        for (int i = 0; i < p->n && use_tma; i++) use_tma = make_map(&maps.inv[i], p->inv_depth[i], p->B, p->H, p->W, FWD_ROWS, 1);
+    }
+    if (use_tma) {
+        cudaFuncSetAttribute(fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FWD_SMEM_BYTES);
+        fwd_kernel<true><<<L.tiles, NT, FWD_SMEM_BYTES, st>>>(fp, maps);
+    } else {
+        memset(&maps, 0, sizeof(maps));
+        cudaFuncSetAttribute(fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, FWD_SMEM_BYTES);
+        fwd_kernel<false><<<L.tiles, NT, FWD_SMEM_BYTES, st>>>(fp, maps);
+    }
     reduce_kernel<<<p->B, 256, 0, st>>>(p->B, p->n, L.tiles_x * L.tiles_y, (long long)p->H * p->W, fp.partials,
                                         (double*)(ws + L.imgsums), (unsigned int*)(ws + L.counter), sums);
     return check_launch("mgvs_forward");
@@ -406,8 +465,20 @@ int mgvs_backward(const MgvsProblem* p, const unsigned char* sel, const double* 
     bp.alpha = p->ssim_weight; bp.oma = p->one_minus_ssim_weight;
     bp.photo_w = p->photometric_weight; bp.smooth_w = p->smoothing_weight;
     bp.tiles_x = L.tiles_x; bp.tiles_y = L.tiles_y;
-    cudaFuncSetAttribute(bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, BWD_SMEM_BYTES);
-    bwd_kernel<<<L.tiles, NT, BWD_SMEM_BYTES, st>>>(bp);
+    BwdMaps maps;
+    bool use_tma = tma_eligible(p);
+    if (use_tma) {
+        use_tma = make_map(&maps.tgt, p->target, 3 * p->B, p->H, p->W, BWD_ROWS, 3);
+        for (int i = 0; i < p->n && use_tma; i++) use_tma = make_map(&maps.inv[i], p->inv_depth[i], p->B, p->H, p->W, BWD_ROWS, 1);
+    }
+    if (use_tma) {
+        cudaFuncSetAttribute(bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, BWD_SMEM_BYTES);
+        bwd_kernel<true><<<L.tiles, NT, BWD_SMEM_BYTES, st>>>(bp, maps);
+    } else {
+        memset(&maps, 0, sizeof(maps));
+        cudaFuncSetAttribute(bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, BWD_SMEM_BYTES);
+        bwd_kernel<false><<<L.tiles, NT, BWD_SMEM_BYTES, st>>>(bp, maps);
+    }
     pose_reduce_kernel<<<p->B * S, 128, 0, st>>>(L.tiles_x * L.tiles_y, bp.pose_partials, p->poses, grad_poses);
     return check_launch("mgvs_backward");
 }

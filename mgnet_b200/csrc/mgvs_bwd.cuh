@@ -35,15 +35,20 @@ struct BwdParams {
     float alpha, oma, photo_w, smooth_w;
     int tiles_x, tiles_y;
 };
+struct BwdMaps {
+    TmaDesc tgt, inv[MAXN];
+};
 
 constexpr int BWD_ROWS = TH + 4;                 // tile+2 halo rows
 constexpr int BWD_CH = BWD_ROWS * PITCH;
-constexpr int BWD_W2 = TW + 4;                   // tile+2 halo width; smem col j <-> image col x0-2+j
+constexpr int BWD_W2 = TW + 4;                   // tile+2 halo width; smem col j <-> image col x0-XOFF+j
 constexpr int BWD_PROWS = TH + 2;                // tile+1 rows (coefficient maps)
 constexpr int BWD_PW = TW + 2;
-constexpr int BWD_MAP = BWD_PROWS * PITCH;       // one coefficient map; col j <-> image col x0-2+j (like fwd)
+constexpr int BWD_MAP = BWD_PROWS * PITCH;       // one coefficient map; col j <-> image col x0-XOFF+j (like fwd)
 constexpr int BWD_PIT = (BWD_PROWS * BWD_PW + NT - 1) / NT;   // stage-B iterations per thread
-constexpr int BWD_SMEM_FLOATS = 3 * BWD_CH + S * 3 * BWD_CH + S * 3 * BWD_MAP + 8 * 24 + 48 + 4 * MAXN;
+constexpr int BWD_TILE3_FLOATS = (3 * BWD_CH + 31) / 32 * 32;
+constexpr int BWD_INV_FLOATS = (BWD_CH + 31) / 32 * 32;
+constexpr int BWD_SMEM_FLOATS = BWD_TILE3_FLOATS + S * 3 * BWD_CH + S * 3 * BWD_MAP + 2 * BWD_INV_FLOATS + 8 * 24 + 48 + 4 * MAXN + 8;
 constexpr int BWD_SMEM_BYTES = BWD_SMEM_FLOATS * 4;
 
 __device__ __forceinline__ void bwd_load_tile(const float* __restrict__ img, float* __restrict__ dst, int x0, int y0,
@@ -55,19 +60,46 @@ __device__ __forceinline__ void bwd_load_tile(const float* __restrict__ img, flo
         int r = idx - ch * (BWD_ROWS * BWD_W2);
         int hr = r / BWD_W2, hc = r - hr * BWD_W2;
         int v = reflect_idx(y0 - 2 + hr, H), u = reflect_idx(x0 - 2 + hc, W);
-        dst[ch * BWD_CH + hr * PITCH + hc] = __ldg(img + ch * HW + v * W + u);
+        dst[ch * BWD_CH + hr * PITCH + XOFF - 2 + hc] = __ldg(img + ch * HW + v * W + u);
     }
 }
 
-__global__ void __launch_bounds__(NT, 2) bwd_kernel(const BwdParams p)
+// weighted 3x3 box adjoint of one coefficient map for 4 adjacent outputs (reflect-pad multiplicities);
+// the unweighted version is used by tiles that do not touch the image border
+template <bool WEIGHTED>
+__device__ __forceinline__ void box_adjoint4(const float* __restrict__ mp, const float rwgt[3], const float (*cwgt)[3], float out[4])
 {
-    extern __shared__ __align__(16) float smem[];
+    float col[6];
+#pragma unroll
+    for (int dy = 0; dy < 3; dy++) {
+        const float* rr = mp + dy * PITCH;               // mp -> [map row of image row v-1][my output 0]
+        float4 a = *reinterpret_cast<const float4*>(rr);
+        float r6[6] = {rr[-1], a.x, a.y, a.z, a.w, rr[4]};
+#pragma unroll
+        for (int j = 0; j < 6; j++) {
+            if (WEIGHTED) col[j] = dy == 0 ? rwgt[0] * r6[j] : fmaf(rwgt[dy], r6[j], col[j]);
+            else col[j] = dy == 0 ? r6[j] : col[j] + r6[j];
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        if (WEIGHTED) out[k] = cwgt[k][0] * col[k] + cwgt[k][1] * col[k + 1] + cwgt[k][2] * col[k + 2];
+        else out[k] = (col[k] + col[k + 1]) + col[k + 2];
+    }
+}
+
+template <bool USE_TMA>
+__global__ void __launch_bounds__(NT, 2) bwd_kernel(const BwdParams p, const __grid_constant__ BwdMaps maps)
+{
+    extern __shared__ __align__(128) float smem[];
     float* sY = smem;                               // [3][BWD_ROWS][PITCH]
-    float* sX = sY + 3 * BWD_CH;                    // [S][3][BWD_ROWS][PITCH]
+    float* sX = sY + BWD_TILE3_FLOATS;              // [S][3][BWD_ROWS][PITCH]
     float* sCo = sX + S * 3 * BWD_CH;               // [S][3 maps][BWD_PROWS][PITCH]  (one channel at a time)
-    float* sRed = sCo + S * 3 * BWD_MAP;            // [8 warps][24]
+    float* sInv = sCo + S * 3 * BWD_MAP;            // [2][BWD_ROWS][PITCH] inverse-depth ring (TMA path)
+    float* sRed = sInv + 2 * BWD_INV_FLOATS;        // [8 warps][24]
     float* sCam = sRed + 8 * 24;                    // 48
-    float* sSm = sCam + 48;                         // [n][4]: inv_c/Nx-scale, inv_c/Ny-scale, mean_term, unused
+    float* sSm = sCam + 48;                         // [n][4]: Ws/(Nx c), Ws/(Ny c), mean term, unused
+    uint64_t* sBar = reinterpret_cast<uint64_t*>(sSm + 4 * MAXN);   // [0] target tile, [1],[2] inverse-depth ring
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int tile = blockIdx.x;
@@ -80,6 +112,15 @@ __global__ void __launch_bounds__(NT, 2) bwd_kernel(const BwdParams p)
     const int tx = tid & 15, ty = tid >> 4;
     const int u0 = x0 + 4 * tx, v = y0 + ty;
 
+    const bool border = (x0 == 0) || (y0 == 0) || (x0 + TW + 1 >= W) || (y0 + TH + 1 >= H);
+    if (USE_TMA && tid == 0) {
+        tma::mbar_init(sBar + 0, 1); tma::mbar_init(sBar + 1, 1); tma::mbar_init(sBar + 2, 1);
+        tma::fence_barrier_init();
+        tma::mbar_expect_tx(sBar + 0, 3 * BWD_CH * 4);
+        tma::load_3d(sY, &maps.tgt, x0 - XOFF, y0 - 2, 3 * b, sBar + 0);
+        tma::mbar_expect_tx(sBar + 1, BWD_CH * 4);
+        tma::load_3d(sInv, &maps.inv[0], x0 - XOFF, y0 - 2, b, sBar + 1);
+    }
     if (tid < 48) sCam[tid] = reinterpret_cast<const float*>(p.cams + b)[tid];
     const int nq = 4 * p.n + 3;
     const double Ntot = p.sums[p.n], Nx = p.sums[3 * p.n + 1], Ny = p.sums[3 * p.n + 2];
@@ -96,8 +137,17 @@ __global__ void __launch_bounds__(NT, 2) bwd_kernel(const BwdParams p)
         sSm[tid * 4 + 1] = (float)(Ws / (Ny * c));
         sSm[tid * 4 + 2] = active ? (float)(-Ws * A / (c * c * (double)HW)) : 0.f;
     }
-    bwd_load_tile(p.tgt + (size_t)b * 3 * HW, sY, x0, y0, H, W, tid);
-    __syncthreads();
+    if (USE_TMA) {
+        __syncthreads();                 // barrier init, camera table and smoothness constants visible
+        tma::mbar_wait(sBar + 0, 0);
+        if (border) {
+            patch_reflect<2, BWD_ROWS>(sY, 3, BWD_CH, x0, y0, H, W, tid, NT);
+            __syncthreads();
+        }
+    } else {
+        bwd_load_tile(p.tgt + (size_t)b * 3 * HW, sY, x0, y0, H, W, tid);
+        __syncthreads();
+    }
 
     const float* K = sCam;
     const float* Kinv = sCam + 9;
@@ -111,10 +161,22 @@ __global__ void __launch_bounds__(NT, 2) bwd_kernel(const BwdParams p)
     const float* src1 = p.src[1] + (size_t)b * 3 * HW;
 
     bool valid[4], msk[4];
+    {
+        unsigned mw = 0x01010101u;
+        if (p.mask != nullptr && v < H) {
+            const unsigned char* mp = p.mask + (size_t)b * HW + (size_t)v * W + u0;
+            if (u0 + 3 < W && ((W & 3) == 0)) mw = *reinterpret_cast<const unsigned*>(mp);
+            else {
+                mw = 0;
 #pragma unroll
-    for (int k = 0; k < 4; k++) {
-        valid[k] = (v < H) && (u0 + k < W);
-        msk[k] = valid[k] && (p.mask == nullptr || p.mask[(size_t)b * HW + (size_t)min(v, H - 1) * W + min(u0 + k, W - 1)] != 0);
+                for (int k = 0; k < 4; k++) if (u0 + k < W) mw |= (unsigned)(mp[k] != 0) << (8 * k);
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            valid[k] = (v < H) && (u0 + k < W);
+            msk[k] = valid[k] && ((mw >> (8 * k)) & 0xffu) != 0;
+        }
     }
     // reflect-pad multiplicities of the box adjoint: tap (q+d) counts twice when its padded twin folds onto q
     float rwgt[3], cwgt[4][3];
@@ -139,13 +201,24 @@ __global__ void __launch_bounds__(NT, 2) bwd_kernel(const BwdParams p)
         const float* inv = p.inv[i] + (size_t)b * HW;
         const unsigned char* sel = p.sel + ((size_t)i * p.B + b) * HW;
 
+        const float* sI = sInv + (i & 1) * BWD_INV_FLOATS;
+        if (USE_TMA) {
+            if (tid == 0 && i + 1 < p.n) {
+                tma::fence_proxy_async();
+                tma::mbar_expect_tx(sBar + 1 + ((i + 1) & 1), BWD_CH * 4);
+                tma::load_3d(sInv + ((i + 1) & 1) * BWD_INV_FLOATS, &maps.inv[i + 1], x0 - XOFF, y0 - 2, b, sBar + 1 + ((i + 1) & 1));
+            }
+            tma::mbar_wait(sBar + 1 + (i & 1), (i >> 1) & 1);
+        }
         // ---- stage A: warp both sources on tile+2 ----
         for (int h = tid; h < BWD_ROWS * BWD_W2; h += NT) {
             int hr = h / BWD_W2, hc = h - hr * BWD_W2;
-            int pv = reflect_idx(y0 - 2 + hr, H), pu = reflect_idx(x0 - 2 + hc, W);
+            int pv = y0 - 2 + hr, pu = x0 - 2 + hc;
+            if (border) { pv = reflect_idx(pv, H); pu = reflect_idx(pu, W); }
             float r[3], Xc[3];
             exact::ray(Kinv, pu, pv, r);
-            float d = exact::rcp_refined(fmaxf(__ldg(inv + pv * W + pu), 1e-6f));
+            float invv = USE_TMA ? sI[(pv - (y0 - 2)) * PITCH + (pu - (x0 - XOFF))] : __ldg(inv + pv * W + pu);
+            float d = exact::rcp_refined(fmaxf(invv, 1e-6f));
 #pragma unroll
             for (int j = 0; j < 3; j++) Xc[j] = __fmul_rn(r[j], d);
 #pragma unroll
@@ -157,7 +230,7 @@ __global__ void __launch_bounds__(NT, 2) bwd_kernel(const BwdParams p)
                 float wnw = __fmul_rn(c.wN, c.wW), wne = __fmul_rn(c.wN, c.wE), wsw = __fmul_rn(c.wS, c.wW),
                       wse = __fmul_rn(c.wS, c.wE);
                 const float* sp = s == 0 ? src0 : src1;
-                float* dst = sX + s * 3 * BWD_CH + hr * PITCH + hc;
+                float* dst = sX + s * 3 * BWD_CH + hr * PITCH + XOFF - 2 + hc;
 #pragma unroll
                 for (int ch = 0; ch < 3; ch++) {
                     float vals[4];
@@ -200,8 +273,8 @@ __global__ void __launch_bounds__(NT, 2) bwd_kernel(const BwdParams p)
                     unsigned s = psel[it];
                     if (s < 2) {
                         // window rows pr..pr+2, cols pc..pc+2 in tile+2 coordinates
-                        const float* xw = sX + s * 3 * BWD_CH + ch * BWD_CH + pr * PITCH + pc;
-                        const float* yw = sY + ch * BWD_CH + pr * PITCH + pc;
+                        const float* xw = sX + s * 3 * BWD_CH + ch * BWD_CH + pr * PITCH + XOFF - 2 + pc;
+                        const float* yw = sY + ch * BWD_CH + pr * PITCH + XOFF - 2 + pc;
                         float sx, sxx, sxy, sy, syy;
 #pragma unroll
                         for (int dy = 0; dy < 3; dy++)
@@ -221,7 +294,7 @@ __global__ void __launch_bounds__(NT, 2) bwd_kernel(const BwdParams p)
                         exact::Ssim q;
                         (void)exact::ssim_from_sums(sx, sxx, sxy, mu_y, mys, sgy, &q);
                         if (q.loss_raw >= 0.f && q.loss_raw <= 1.f) {      // clamp passes gradient inclusively
-                            float id1 = 1.0f / q.d1, id2 = 1.0f / q.d2;
+                            float id1 = exact::rcp_refined(q.d1), id2 = exact::rcp_refined(q.d2);
                             float idd = id1 * id2;
                             float ds_dmux = 2.f * mu_y * (q.n2 - q.n1) * idd - q.ssim * 2.f * q.mu_x * (id1 - id2);
                             float ds_dexx = -q.ssim * id2;
@@ -231,7 +304,7 @@ __global__ void __launch_bounds__(NT, 2) bwd_kernel(const BwdParams p)
                             cc = cf_ssim * ds_dexy;
                         }
                     }
-                    float* m0 = sCo + pr * PITCH + pc + 1;               // set 0
+                    float* m0 = sCo + pr * PITCH + XOFF - 1 + pc;        // set 0
                     float* m1 = m0 + 3 * BWD_MAP;                        // set 1
                     bool s0 = (s == 0), s1 = (s == 1);
                     m0[0] = s0 ? ca : 0.f; m0[BWD_MAP] = s0 ? cb : 0.f; m0[2 * BWD_MAP] = s0 ? cc : 0.f;
@@ -239,30 +312,20 @@ __global__ void __launch_bounds__(NT, 2) bwd_kernel(const BwdParams p)
                 }
             }
             __syncthreads();
-            // ---- stage C: weighted 3x3 box adjoint for my 4 outputs ----
+            // ---- stage C: 3x3 box adjoint (with reflect-pad multiplicities on border tiles) for my 4 outputs ----
 #pragma unroll
             for (int s = 0; s < S; s++) {
                 float box[3][4];
 #pragma unroll
                 for (int m = 0; m < 3; m++) {
-                    const float* mp = sCo + (s * 3 + m) * BWD_MAP + ty * PITCH + 4 * tx;
-                    float col[6] = {0, 0, 0, 0, 0, 0};
-#pragma unroll
-                    for (int dy = 0; dy < 3; dy++) {
-                        const float4* rr = reinterpret_cast<const float4*>(mp + dy * PITCH);
-                        float4 a = rr[0], bq = rr[1];
-                        float r6[6] = {a.y, a.z, a.w, bq.x, bq.y, bq.z};
-#pragma unroll
-                        for (int j = 0; j < 6; j++) col[j] = fmaf(rwgt[dy], r6[j], col[j]);
-                    }
-#pragma unroll
-                    for (int k = 0; k < 4; k++)
-                        box[m][k] = cwgt[k][0] * col[k] + cwgt[k][1] * col[k + 1] + cwgt[k][2] * col[k + 2];
+                    const float* mp = sCo + (s * 3 + m) * BWD_MAP + ty * PITCH + XOFF + 4 * tx;
+                    if (border) box_adjoint4<true>(mp, rwgt, cwgt, box[m]);
+                    else box_adjoint4<false>(mp, rwgt, cwgt, box[m]);
                 }
 #pragma unroll
                 for (int k = 0; k < 4; k++) {
-                    float xq = sX[s * 3 * BWD_CH + ch * BWD_CH + (ty + 2) * PITCH + 4 * tx + 2 + k];
-                    float yq = sY[ch * BWD_CH + (ty + 2) * PITCH + 4 * tx + 2 + k];
+                    float xq = sX[s * 3 * BWD_CH + ch * BWD_CH + (ty + 2) * PITCH + XOFF + 4 * tx + k];
+                    float yq = sY[ch * BWD_CH + (ty + 2) * PITCH + XOFF + 4 * tx + k];
                     G[s][ch][k] = box[0][k] + xq * box[1][k] + yq * box[2][k];
                 }
             }
@@ -285,31 +348,32 @@ __global__ void __launch_bounds__(NT, 2) bwd_kernel(const BwdParams p)
                 int u = u0 + k;
                 if (valid[k]) {
                     g = mt;
-                    const float* yc = sY + (ty + 2) * PITCH + 4 * tx + 2 + k;
-                    float ic = __ldg(inv + (size_t)v * W + u);
+                    const float* yc = sY + (ty + 2) * PITCH + XOFF + 4 * tx + k;
+                    const float* iq = sI + (ty + 2) * PITCH + XOFF + 4 * tx + k;
+                    float ic = USE_TMA ? iq[0] : __ldg(inv + (size_t)v * W + u);
                     // pair (p, p+1): owner mask is the LEFT pixel (loss.py:285)
                     if (u + 1 < W && msk[k]) {
                         float a = fabsf(yc[0] - yc[1]) + fabsf(yc[BWD_CH] - yc[BWD_CH + 1]) + fabsf(yc[2 * BWD_CH] - yc[2 * BWD_CH + 1]);
                         float w = expf(-exact::div3(a));
-                        float df = ic - __ldg(inv + (size_t)v * W + u + 1);
+                        float df = ic - (USE_TMA ? iq[1] : __ldg(inv + (size_t)v * W + u + 1));
                         g += kx * w * (df > 0.f ? 1.f : (df < 0.f ? -1.f : 0.f));
                     }
                     if (u > 0 && (p.mask == nullptr || p.mask[(size_t)b * HW + (size_t)v * W + u - 1] != 0)) {
                         float a = fabsf(yc[-1] - yc[0]) + fabsf(yc[BWD_CH - 1] - yc[BWD_CH]) + fabsf(yc[2 * BWD_CH - 1] - yc[2 * BWD_CH]);
                         float w = expf(-exact::div3(a));
-                        float df = __ldg(inv + (size_t)v * W + u - 1) - ic;
+                        float df = (USE_TMA ? iq[-1] : __ldg(inv + (size_t)v * W + u - 1)) - ic;
                         g -= kx * w * (df > 0.f ? 1.f : (df < 0.f ? -1.f : 0.f));
                     }
                     if (v + 1 < H && msk[k]) {
                         float a = fabsf(yc[0] - yc[PITCH]) + fabsf(yc[BWD_CH] - yc[BWD_CH + PITCH]) + fabsf(yc[2 * BWD_CH] - yc[2 * BWD_CH + PITCH]);
                         float w = expf(-exact::div3(a));
-                        float df = ic - __ldg(inv + (size_t)(v + 1) * W + u);
+                        float df = ic - (USE_TMA ? iq[PITCH] : __ldg(inv + (size_t)(v + 1) * W + u));
                         g += ky * w * (df > 0.f ? 1.f : (df < 0.f ? -1.f : 0.f));
                     }
                     if (v > 0 && (p.mask == nullptr || p.mask[(size_t)b * HW + (size_t)(v - 1) * W + u] != 0)) {
                         float a = fabsf(yc[-PITCH] - yc[0]) + fabsf(yc[BWD_CH - PITCH] - yc[BWD_CH]) + fabsf(yc[2 * BWD_CH - PITCH] - yc[2 * BWD_CH]);
                         float w = expf(-exact::div3(a));
-                        float df = __ldg(inv + (size_t)(v - 1) * W + u) - ic;
+                        float df = (USE_TMA ? iq[-PITCH] : __ldg(inv + (size_t)(v - 1) * W + u)) - ic;
                         g -= ky * w * (df > 0.f ? 1.f : (df < 0.f ? -1.f : 0.f));
                     }
                 }
@@ -327,8 +391,8 @@ __global__ void __launch_bounds__(NT, 2) bwd_kernel(const BwdParams p)
                 bool selme = msk[k] && (p.automask ? (code == 2u * s) : (code == (unsigned)s));
                 float g0 = G[s][0][k], g1 = G[s][1][k], g2 = G[s][2][k];
                 if (selme) {
-                    const float* xq = sX + s * 3 * BWD_CH + (ty + 2) * PITCH + 4 * tx + 2 + k;
-                    const float* yq = sY + (ty + 2) * PITCH + 4 * tx + 2 + k;
+                    const float* xq = sX + s * 3 * BWD_CH + (ty + 2) * PITCH + XOFF + 4 * tx + k;
+                    const float* yq = sY + (ty + 2) * PITCH + XOFF + 4 * tx + k;
                     float d0 = xq[0] - yq[0], d1 = xq[BWD_CH] - yq[BWD_CH], d2 = xq[2 * BWD_CH] - yq[2 * BWD_CH];
                     g0 += cf_l1 * (d0 > 0.f ? 1.f : (d0 < 0.f ? -1.f : 0.f));
                     g1 += cf_l1 * (d1 > 0.f ? 1.f : (d1 < 0.f ? -1.f : 0.f));
@@ -338,7 +402,7 @@ __global__ void __launch_bounds__(NT, 2) bwd_kernel(const BwdParams p)
                 int u = u0 + k;
                 float r[3], Xc[3];
                 exact::ray(Kinv, u, v, r);
-                float invq = __ldg(inv + (size_t)v * W + u);
+                float invq = USE_TMA ? sI[(ty + 2) * PITCH + XOFF + 4 * tx + k] : __ldg(inv + (size_t)v * W + u);
                 float d = exact::rcp_refined(fmaxf(invq, 1e-6f));
 #pragma unroll
                 for (int j = 0; j < 3; j++) Xc[j] = __fmul_rn(r[j], d);
@@ -357,7 +421,7 @@ __global__ void __launch_bounds__(NT, 2) bwd_kernel(const BwdParams p)
                     giy += gch[ch] * ((sw - nw) * c.wW + (se - ne) * c.wE);
                 }
                 // projection adjoint (App. B-5)
-                float iz = 1.0f / pr.Z;
+                float iz = exact::rcp_refined(pr.Z);
                 float gP0 = gix * iz, gP1 = giy * iz;
                 float gP2 = (pr.Pz >= 1e-5f) ? -(gix * pr.ax + giy * pr.ay) * iz : 0.f;
                 float gX0 = K[0] * gP0 + K[3] * gP1 + K[6] * gP2;

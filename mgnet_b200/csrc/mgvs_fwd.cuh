@@ -27,10 +27,17 @@ struct FwdParams {
     int tiles_x, tiles_y;
 };
 
+struct FwdMaps {
+    TmaDesc tgt, src[S], inv[MAXN];
+};
+
 constexpr int FWD_ROWS = TH + 2;                 // halo rows
 constexpr int FWD_CH = FWD_ROWS * PITCH;         // floats per channel plane in smem
 constexpr int FWD_HALO_W = TW + 2;
-constexpr int FWD_SMEM_FLOATS = 3 * FWD_CH /*Y*/ + S * 3 * FWD_CH /*X*/ + 9 * TH * TW /*Y stats*/ + 8 * 8 /*red*/ + 48 /*cam*/;
+constexpr int FWD_TILE3_FLOATS = (3 * FWD_CH + 31) / 32 * 32;      // one 3-channel tile, padded to 128 bytes
+constexpr int FWD_INV_FLOATS = (FWD_CH + 31) / 32 * 32;            // one inverse-depth tile
+constexpr int FWD_SMEM_FLOATS = FWD_TILE3_FLOATS /*Y*/ + S * FWD_TILE3_FLOATS /*X*/ + 2 * FWD_INV_FLOATS /*inv ring*/ +
+                                9 * TH * TW /*Y stats*/ + 8 * 8 /*red*/ + 48 /*cam*/ + 8 /*3 mbarriers*/;
 constexpr int FWD_SMEM_BYTES = FWD_SMEM_FLOATS * 4;
 
 // Loads a [3,H,W] image tile with 1-pixel halo (reflect-indexed) into smem planes.
@@ -43,12 +50,13 @@ __device__ __forceinline__ void fwd_load_tile(const float* __restrict__ img, flo
         int r = idx - ch * (FWD_ROWS * FWD_HALO_W);
         int hr = r / FWD_HALO_W, hc = r - hr * FWD_HALO_W;
         int v = reflect_idx(y0 - 1 + hr, H), u = reflect_idx(x0 - 1 + hc, W);
-        dst[ch * FWD_CH + hr * PITCH + 1 + hc] = __ldg(img + ch * HW + v * W + u);
+        dst[ch * FWD_CH + hr * PITCH + XOFF - 1 + hc] = __ldg(img + ch * HW + v * W + u);
     }
 }
 
 // Photometric loss (alpha*mean_c SSIM + (1-alpha)*mean_c L1, loss.py:186-194) of 4 adjacent outputs.
-// xs, ys: smem planes of the estimate and the target, pointing at [ch 0][row ty][col 4*tx] (16B aligned);
+// xs, ys: smem planes of the estimate and the target, pointing at [ch 0][halo row ty][my output 0]
+// (16B aligned); the 3x3 windows of the 4 outputs span columns -1..4 of rows 0..2 from there.
 // yst: target statistics at [0][ty][4*tx].
 __device__ __forceinline__ void photometric4(const float* __restrict__ xs, const float* __restrict__ ys,
                                              const float* __restrict__ yst, float alpha, float oma, float out[4])
@@ -59,12 +67,11 @@ __device__ __forceinline__ void photometric4(const float* __restrict__ xs, const
         float sx[4], sxx[4], sxy[4], l1[4];
 #pragma unroll
         for (int dy = 0; dy < 3; dy++) {
-            const float4* xr = reinterpret_cast<const float4*>(xs + ch * FWD_CH + dy * PITCH);
-            const float4* yr = reinterpret_cast<const float4*>(ys + ch * FWD_CH + dy * PITCH);
-            float4 xa = xr[0], xb = xr[1], ya = yr[0], yb = yr[1];
-            // window columns 4tx+1 .. 4tx+6
-            float x6[6] = {xa.y, xa.z, xa.w, xb.x, xb.y, xb.z};
-            float y6[6] = {ya.y, ya.z, ya.w, yb.x, yb.y, yb.z};
+            const float* xr = xs + ch * FWD_CH + dy * PITCH;
+            const float* yr = ys + ch * FWD_CH + dy * PITCH;
+            float4 xm = *reinterpret_cast<const float4*>(xr), ym = *reinterpret_cast<const float4*>(yr);
+            float x6[6] = {xr[-1], xm.x, xm.y, xm.z, xm.w, xr[4]};
+            float y6[6] = {yr[-1], ym.x, ym.y, ym.z, ym.w, yr[4]};
             float xx6[6], xy6[6];
 #pragma unroll
             for (int j = 0; j < 6; j++) { xx6[j] = __fmul_rn(x6[j], x6[j]); xy6[j] = __fmul_rn(x6[j], y6[j]); }
@@ -95,14 +102,17 @@ __device__ __forceinline__ void photometric4(const float* __restrict__ xs, const
         out[k] = __fadd_rn(__fmul_rn(alpha, exact::div3(ssum[k])), __fmul_rn(oma, exact::div3(lsum[k])));
 }
 
-__global__ void __launch_bounds__(NT, 2) fwd_kernel(const FwdParams p)
+template <bool USE_TMA>
+__global__ void __launch_bounds__(NT, 2) fwd_kernel(const FwdParams p, const __grid_constant__ FwdMaps maps)
 {
-    extern __shared__ __align__(16) float smem[];
+    extern __shared__ __align__(128) float smem[];
     float* sY = smem;
-    float* sX = sY + 3 * FWD_CH;            // [S][3][rows][PITCH]
-    float* sYst = sX + S * 3 * FWD_CH;      // [9][TH][TW]
-    float* sRed = sYst + 9 * TH * TW;       // [8 warps][8]
-    float* sCam = sRed + 64;                // 48 floats
+    float* sX = sY + FWD_TILE3_FLOATS;          // [S][3][rows][PITCH] (each source tile 128B aligned)
+    float* sInv = sX + S * FWD_TILE3_FLOATS;    // [2][rows][PITCH] inverse-depth ring (TMA path)
+    float* sYst = sInv + 2 * FWD_INV_FLOATS;    // [9][TH][TW]
+    float* sRed = sYst + 9 * TH * TW;           // [8 warps][8]
+    float* sCam = sRed + 64;                    // 48 floats
+    uint64_t* sBar = reinterpret_cast<uint64_t*>(sCam + 48);   // [0] image tiles, [1],[2] inverse-depth ring
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int tile = blockIdx.x;
@@ -115,11 +125,35 @@ __global__ void __launch_bounds__(NT, 2) fwd_kernel(const FwdParams p)
     const int tx = tid & 15, ty = tid >> 4;
     const int u0 = x0 + 4 * tx, v = y0 + ty;     // this thread's 4 outputs: (v, u0..u0+3)
 
-    if (tid < 48) sCam[tid] = reinterpret_cast<const float*>(p.cams + b)[tid];
-    fwd_load_tile(p.tgt + (size_t)b * 3 * HW, sY, x0, y0, H, W, tid);
-    fwd_load_tile(p.src[0] + (size_t)b * 3 * HW, sX, x0, y0, H, W, tid);
-    fwd_load_tile(p.src[1] + (size_t)b * 3 * HW, sX + 3 * FWD_CH, x0, y0, H, W, tid);
-    __syncthreads();
+    const bool border = (x0 == 0) || (y0 == 0) || (x0 + TW >= W) || (y0 + TH >= H);
+    if (USE_TMA) {
+        if (tid == 0) {
+            tma::mbar_init(sBar + 0, 1); tma::mbar_init(sBar + 1, 1); tma::mbar_init(sBar + 2, 1);
+            tma::fence_barrier_init();
+            tma::mbar_expect_tx(sBar + 0, 3 * 3 * FWD_CH * 4);
+            tma::load_3d(sY, &maps.tgt, x0 - XOFF, y0 - 1, 3 * b, sBar + 0);
+            tma::load_3d(sX, &maps.src[0], x0 - XOFF, y0 - 1, 3 * b, sBar + 0);
+            tma::load_3d(sX + FWD_TILE3_FLOATS, &maps.src[1], x0 - XOFF, y0 - 1, 3 * b, sBar + 0);
+            tma::mbar_expect_tx(sBar + 1, FWD_CH * 4);
+            tma::load_3d(sInv, &maps.inv[0], x0 - XOFF, y0 - 1, b, sBar + 1);
+        }
+        if (tid < 48) sCam[tid] = reinterpret_cast<const float*>(p.cams + b)[tid];
+        __syncthreads();                 // barrier init + camera table visible
+        tma::mbar_wait(sBar + 0, 0);
+        if (border) {                    // CTA-uniform
+            // the three tiles are contiguous planes of FWD_TILE3_FLOATS / FWD_CH floats: patch them in one go
+            patch_reflect<1, FWD_ROWS>(sY, 3, FWD_CH, x0, y0, H, W, tid, NT);
+            patch_reflect<1, FWD_ROWS>(sX, 3, FWD_CH, x0, y0, H, W, tid, NT);
+            patch_reflect<1, FWD_ROWS>(sX + FWD_TILE3_FLOATS, 3, FWD_CH, x0, y0, H, W, tid, NT);
+            __syncthreads();
+        }
+    } else {
+        if (tid < 48) sCam[tid] = reinterpret_cast<const float*>(p.cams + b)[tid];
+        fwd_load_tile(p.tgt + (size_t)b * 3 * HW, sY, x0, y0, H, W, tid);
+        fwd_load_tile(p.src[0] + (size_t)b * 3 * HW, sX, x0, y0, H, W, tid);
+        fwd_load_tile(p.src[1] + (size_t)b * 3 * HW, sX + FWD_TILE3_FLOATS, x0, y0, H, W, tid);
+        __syncthreads();
+    }
 
     const float* K = sCam;
     const float* Kinv = sCam + 9;
@@ -129,13 +163,25 @@ __global__ void __launch_bounds__(NT, 2) fwd_kernel(const FwdParams p)
     // validity and mask of the 4 outputs
     bool valid[4];
     bool msk[4];
+    {
+        unsigned mw = 0x01010101u;
+        if (p.mask != nullptr && v < H) {
+            const unsigned char* mp = p.mask + (size_t)b * HW + (size_t)v * W + u0;
+            if (u0 + 3 < W && ((W & 3) == 0)) mw = *reinterpret_cast<const unsigned*>(mp);
+            else {
+                mw = 0;
 #pragma unroll
-    for (int k = 0; k < 4; k++) {
-        valid[k] = (v < H) && (u0 + k < W);
-        msk[k] = valid[k] && (p.mask == nullptr || p.mask[(size_t)b * HW + (size_t)min(v, H - 1) * W + min(u0 + k, W - 1)] != 0);
+                for (int k = 0; k < 4; k++) if (u0 + k < W) mw |= (unsigned)(mp[k] != 0) << (8 * k);
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            valid[k] = (v < H) && (u0 + k < W);
+            msk[k] = valid[k] && ((mw >> (8 * k)) & 0xffu) != 0;
+        }
     }
 
-    const float* ys_t = sY + ty * PITCH + 4 * tx;
+    const float* ys_t = sY + ty * PITCH + XOFF + 4 * tx;      // [ch 0][halo row ty][my output 0], 16B aligned
     float* yst_t = sYst + ty * TW + 4 * tx;
     // target statistics for my 4 outputs (shared by all 2+2n photometric evaluations)
 #pragma unroll
@@ -143,9 +189,9 @@ __global__ void __launch_bounds__(NT, 2) fwd_kernel(const FwdParams p)
         float sy[4], syy[4];
 #pragma unroll
         for (int dy = 0; dy < 3; dy++) {
-            const float4* yr = reinterpret_cast<const float4*>(ys_t + ch * FWD_CH + dy * PITCH);
-            float4 ya = yr[0], yb = yr[1];
-            float y6[6] = {ya.y, ya.z, ya.w, yb.x, yb.y, yb.z}, yy6[6];
+            const float* yr = ys_t + ch * FWD_CH + dy * PITCH;
+            float4 ym = *reinterpret_cast<const float4*>(yr);
+            float y6[6] = {yr[-1], ym.x, ym.y, ym.z, ym.w, yr[4]}, yy6[6];
 #pragma unroll
             for (int j = 0; j < 6; j++) yy6[j] = __fmul_rn(y6[j], y6[j]);
 #pragma unroll
@@ -172,8 +218,8 @@ __global__ void __launch_bounds__(NT, 2) fwd_kernel(const FwdParams p)
     // identity-reprojection losses (un-warped source vs target), once per tile
     float lid0[4] = {0, 0, 0, 0}, lid1[4] = {0, 0, 0, 0};
     if (p.automask) {
-        photometric4(sX + ty * PITCH + 4 * tx, ys_t, yst_t, p.alpha, p.oma, lid0);
-        photometric4(sX + 3 * FWD_CH + ty * PITCH + 4 * tx, ys_t, yst_t, p.alpha, p.oma, lid1);
+        photometric4(sX + ty * PITCH + XOFF + 4 * tx, ys_t, yst_t, p.alpha, p.oma, lid0);
+        photometric4(sX + FWD_TILE3_FLOATS + ty * PITCH + XOFF + 4 * tx, ys_t, yst_t, p.alpha, p.oma, lid1);
     }
 
     // edge-aware smoothness weights exp(-mean_c |dI|) (depth.py:23-24), premultiplied by mask/validity
@@ -181,7 +227,7 @@ __global__ void __launch_bounds__(NT, 2) fwd_kernel(const FwdParams p)
     float cntN = 0.f, cntX = 0.f, cntY = 0.f;
 #pragma unroll
     for (int k = 0; k < 4; k++) {
-        const float* yc = sY + (ty + 1) * PITCH + 4 * tx + 2 + k;
+        const float* yc = sY + (ty + 1) * PITCH + XOFF + 4 * tx + k;
         float ax = 0.f, ay = 0.f;
 #pragma unroll
         for (int ch = 0; ch < 3; ch++) {
@@ -207,13 +253,27 @@ __global__ void __launch_bounds__(NT, 2) fwd_kernel(const FwdParams p)
 
     for (int i = 0; i < p.n; i++) {
         const float* inv = p.inv[i] + (size_t)b * HW;
+        const float* sI = sInv + (i & 1) * FWD_INV_FLOATS;
+        if (USE_TMA) {
+            // prefetch the next scale's inverse-depth tile into the other ring slot (its last readers
+            // finished before the barrier that ended the previous scale), then wait for this scale's tile
+            if (tid == 0 && i + 1 < p.n) {
+                tma::fence_proxy_async();
+                tma::mbar_expect_tx(sBar + 1 + ((i + 1) & 1), FWD_CH * 4);
+                tma::load_3d(sInv + ((i + 1) & 1) * FWD_INV_FLOATS, &maps.inv[i + 1], x0 - XOFF, y0 - 1, b, sBar + 1 + ((i + 1) & 1));
+            }
+            tma::mbar_wait(sBar + 1 + (i & 1), (i >> 1) & 1);
+        }
         // ---- stage 1: warp both sources at every halo pixel ----
         for (int h = tid; h < FWD_ROWS * FWD_HALO_W; h += NT) {
             int hr = h / FWD_HALO_W, hc = h - hr * FWD_HALO_W;
-            int pv = reflect_idx(y0 - 1 + hr, H), pu = reflect_idx(x0 - 1 + hc, W);
+            int pv = y0 - 1 + hr, pu = x0 - 1 + hc;
+            if (border) { pv = reflect_idx(pv, H); pu = reflect_idx(pu, W); }
             float r[3], Xc[3];
             exact::ray(Kinv, pu, pv, r);
-            float d = exact::rcp_refined(fmaxf(__ldg(inv + pv * W + pu), 1e-6f));   // depth.py:15
+            // the reflected pixel lies inside the loaded box, so the zero-filled halo is never read
+            float invv = USE_TMA ? sI[(pv - (y0 - 1)) * PITCH + (pu - (x0 - XOFF))] : __ldg(inv + pv * W + pu);
+            float d = exact::rcp_refined(fmaxf(invv, 1e-6f));   // depth.py:15
 #pragma unroll
             for (int j = 0; j < 3; j++) Xc[j] = __fmul_rn(r[j], d);
 #pragma unroll
@@ -225,7 +285,7 @@ __global__ void __launch_bounds__(NT, 2) fwd_kernel(const FwdParams p)
                 float wnw = __fmul_rn(c.wN, c.wW), wne = __fmul_rn(c.wN, c.wE), wsw = __fmul_rn(c.wS, c.wW),
                       wse = __fmul_rn(c.wS, c.wE);
                 const float* sp = s == 0 ? src0 : src1;
-                float* dst = sX + s * 3 * FWD_CH + hr * PITCH + 1 + hc;
+                float* dst = sX + s * FWD_TILE3_FLOATS + hr * PITCH + XOFF - 1 + hc;
 #pragma unroll
                 for (int ch = 0; ch < 3; ch++) {
                     float vals[4];
@@ -237,8 +297,8 @@ __global__ void __launch_bounds__(NT, 2) fwd_kernel(const FwdParams p)
 
         // ---- stage 2: photometric maps, min/argmin, smoothness ----
         float lw0[4], lw1[4];
-        photometric4(sX + ty * PITCH + 4 * tx, ys_t, yst_t, p.alpha, p.oma, lw0);
-        photometric4(sX + 3 * FWD_CH + ty * PITCH + 4 * tx, ys_t, yst_t, p.alpha, p.oma, lw1);
+        photometric4(sX + ty * PITCH + XOFF + 4 * tx, ys_t, yst_t, p.alpha, p.oma, lw0);
+        photometric4(sX + FWD_TILE3_FLOATS + ty * PITCH + XOFF + 4 * tx, ys_t, yst_t, p.alpha, p.oma, lw1);
         float photo = 0.f;
         unsigned selw = 0;
 #pragma unroll
@@ -267,12 +327,13 @@ __global__ void __launch_bounds__(NT, 2) fwd_kernel(const FwdParams p)
         float smx = 0.f, smy = 0.f, isum = 0.f;
         if (v < H) {
             const float* ir = inv + (size_t)v * W;
+            const float* si = sI + (ty + 1) * PITCH + XOFF + 4 * tx;   // my 4 outputs in the smem tile
             float c4[5];
 #pragma unroll
-            for (int k = 0; k < 5; k++) c4[k] = (u0 + k < W) ? __ldg(ir + u0 + k) : 0.f;
+            for (int k = 0; k < 5; k++) c4[k] = USE_TMA ? si[k] : ((u0 + k < W) ? __ldg(ir + u0 + k) : 0.f);
 #pragma unroll
             for (int k = 0; k < 4; k++) {
-                float below = (v + 1 < H && u0 + k < W) ? __ldg(ir + W + u0 + k) : 0.f;
+                float below = USE_TMA ? si[PITCH + k] : ((v + 1 < H && u0 + k < W) ? __ldg(ir + W + u0 + k) : 0.f);
                 smx += wxm[k] * fabsf(c4[k] - c4[k + 1]);
                 smy += wym[k] * fabsf(c4[k] - below);
                 isum += valid[k] ? c4[k] : 0.f;

@@ -134,6 +134,7 @@ class _ViewSynthesisLoss(torch.autograd.Function):
         saved = [poses, camera, tgt, prev, nxt, sel, sums, ws] + ([mask] if mask is not None else []) + list(inv)
         ctx.save_for_backward(*saved)
         ctx.mark_non_differentiable(sel)
+        ctx.set_materialize_grads(False)
         lp, ls = losses.unbind(0)
         return lp, ls, sel
 
