@@ -13,7 +13,7 @@ import subprocess
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _CSRC = os.path.join(_HERE, "csrc")
-LIB_PATH = os.path.join(_HERE, "libmgvs.so")
+LIB_PATH = os.environ.get("MGVS_LIB_PATH") or os.path.join(_HERE, "libmgvs.so")   # override: kernel-variant experiments only
 MAX_SCALES = 8
 NUM_SOURCES = 2
 
@@ -47,6 +47,8 @@ def _sources():
 
 
 def needs_build() -> bool:
+    if os.environ.get("MGVS_LIB_PATH"):
+        return False
     if not os.path.isfile(LIB_PATH):
         return True
     t = os.path.getmtime(LIB_PATH)

@@ -48,7 +48,8 @@ constexpr int BWD_MAP = BWD_PROWS * PITCH;       // one coefficient map; col j <
 constexpr int BWD_PIT = (BWD_PROWS * BWD_PW + NT - 1) / NT;   // stage-B iterations per thread
 constexpr int BWD_TILE3_FLOATS = (3 * BWD_CH + 31) / 32 * 32;
 constexpr int BWD_INV_FLOATS = (BWD_CH + 31) / 32 * 32;
-constexpr int BWD_SMEM_FLOATS = BWD_TILE3_FLOATS + S * 3 * BWD_CH + S * 3 * BWD_MAP + 2 * BWD_INV_FLOATS + 8 * 24 + 48 + 4 * MAXN + 8;
+constexpr int BWD_NW = 13;                       // per-thread edge-aware weights kept across scales (see prologue)
+constexpr int BWD_SMEM_FLOATS = BWD_TILE3_FLOATS + S * 3 * BWD_CH + S * 3 * BWD_MAP + 2 * BWD_INV_FLOATS + BWD_NW * NT + 8 * 24 + 48 + 4 * MAXN + 8;
 constexpr int BWD_SMEM_BYTES = BWD_SMEM_FLOATS * 4;
 
 __device__ __forceinline__ void bwd_load_tile(const float* __restrict__ img, float* __restrict__ dst, int x0, int y0,
@@ -96,7 +97,8 @@ __global__ void __launch_bounds__(NT, 2) bwd_kernel(const BwdParams p, const __g
     float* sX = sY + BWD_TILE3_FLOATS;              // [S][3][BWD_ROWS][PITCH]
     float* sCo = sX + S * 3 * BWD_CH;               // [S][3 maps][BWD_PROWS][PITCH]  (one channel at a time)
     float* sInv = sCo + S * 3 * BWD_MAP;            // [2][BWD_ROWS][PITCH] inverse-depth ring (TMA path)
-    float* sRed = sInv + 2 * BWD_INV_FLOATS;        // [8 warps][24]
+    float* sW = sInv + 2 * BWD_INV_FLOATS;          // [13][NT] masked smoothness weights of my 4 outputs
+    float* sRed = sW + BWD_NW * NT;                 // [8 warps][24]
     float* sCam = sRed + 8 * 24;                    // 48
     float* sSm = sCam + 48;                         // [n][4]: Ws/(Nx c), Ws/(Ny c), mean term, unused
     uint64_t* sBar = reinterpret_cast<uint64_t*>(sSm + 4 * MAXN);   // [0] target tile, [1],[2] inverse-depth ring
@@ -191,6 +193,29 @@ __global__ void __launch_bounds__(NT, 2) bwd_kernel(const BwdParams p, const __g
         cwgt[k][2] = (u + 1 <= W - 1) ? ((u == W - 2) ? 2.f : 1.f) : 0.f;
     }
 
+    // Edge-aware weights exp(-mean_c|dI|) (depth.py:23-24) of the four pixel pairs each output takes part in,
+    // already multiplied by the mask of the pair's owner (left / upper pixel, loss.py:285-286) and zero where
+    // the pair does not exist.  Scale independent: computed once, parked in smem (slot j of thread tid).
+    //   [0..3] pair (q, q+1)   [4] pair (q0-1, q0)   [5..8] pair (q, q+W)   [9..12] pair (q-W, q)
+    {
+        auto wgt = [&](const float* a, const float* b) {
+            float d = (fabsf(a[0] - b[0]) + fabsf(a[BWD_CH] - b[BWD_CH])) + fabsf(a[2 * BWD_CH] - b[2 * BWD_CH]);
+            return expf(-exact::div3(d));
+        };
+        auto mask_at = [&](int vv, int uu) {
+            return vv >= 0 && vv < H && uu >= 0 && uu < W && (p.mask == nullptr || p.mask[(size_t)b * HW + (size_t)vv * W + uu] != 0);
+        };
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const float* yc = sY + (ty + 2) * PITCH + XOFF + 4 * tx + k;
+            int u = u0 + k;
+            sW[(0 + k) * NT + tid] = (msk[k] && u + 1 < W) ? wgt(yc, yc + 1) : 0.f;
+            sW[(5 + k) * NT + tid] = (msk[k] && v + 1 < H) ? wgt(yc, yc + PITCH) : 0.f;
+            sW[(9 + k) * NT + tid] = (valid[k] && mask_at(v - 1, u)) ? wgt(yc - PITCH, yc) : 0.f;
+            if (k == 0) sW[4 * NT + tid] = (valid[0] && mask_at(v, u - 1)) ? wgt(yc - 1, yc) : 0.f;
+        }
+    }
+
     float pacc[S][12];
 #pragma unroll
     for (int s = 0; s < S; s++)
@@ -211,6 +236,7 @@ __global__ void __launch_bounds__(NT, 2) bwd_kernel(const BwdParams p, const __g
             tma::mbar_wait(sBar + 1 + (i & 1), (i >> 1) & 1);
         }
         // ---- stage A: warp both sources on tile+2 ----
+        MGVS_PRAGMA_UNROLL_WARP
         for (int h = tid; h < BWD_ROWS * BWD_W2; h += NT) {
             int hr = h / BWD_W2, hc = h - hr * BWD_W2;
             int pv = y0 - 2 + hr, pu = x0 - 2 + hc;
@@ -342,42 +368,34 @@ __global__ void __launch_bounds__(NT, 2) bwd_kernel(const BwdParams p, const __g
         // smoothness gradient (App. B-6): d/dinv of sum m*w*|inv_p - inv_q| / (N*c) plus the mean term
         {
             const float kx = sSm[i * 4 + 0], ky = sSm[i * 4 + 1], mt = sSm[i * 4 + 2];
+            float ic[6], iu[4], id[4];      // inverse depth: row v cols -1..4, row v-1, row v+1
+            if (USE_TMA) {
+                const float* iq = sI + (ty + 2) * PITCH + XOFF + 4 * tx;
+                float4 c4 = *reinterpret_cast<const float4*>(iq);
+                float4 u4 = *reinterpret_cast<const float4*>(iq - PITCH);
+                float4 d4 = *reinterpret_cast<const float4*>(iq + PITCH);
+                ic[0] = iq[-1]; ic[1] = c4.x; ic[2] = c4.y; ic[3] = c4.z; ic[4] = c4.w; ic[5] = iq[4];
+                iu[0] = u4.x; iu[1] = u4.y; iu[2] = u4.z; iu[3] = u4.w;
+                id[0] = d4.x; id[1] = d4.y; id[2] = d4.z; id[3] = d4.w;
+            } else {
+#pragma unroll
+                for (int k = -1; k < 5; k++) { int u = u0 + k; ic[k + 1] = (v < H && u >= 0 && u < W) ? __ldg(inv + (size_t)v * W + u) : 0.f; }
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    int u = u0 + k;
+                    iu[k] = (v >= 1 && v - 1 < H && u < W) ? __ldg(inv + (size_t)(v - 1) * W + u) : 0.f;
+                    id[k] = (v + 1 < H && u < W) ? __ldg(inv + (size_t)(v + 1) * W + u) : 0.f;
+                }
+            }
+            auto sgn = [](float d) { return d > 0.f ? 1.f : (d < 0.f ? -1.f : 0.f); };
+            float wl = sW[4 * NT + tid];
 #pragma unroll
             for (int k = 0; k < 4; k++) {
-                float g = 0.f;
-                int u = u0 + k;
-                if (valid[k]) {
-                    g = mt;
-                    const float* yc = sY + (ty + 2) * PITCH + XOFF + 4 * tx + k;
-                    const float* iq = sI + (ty + 2) * PITCH + XOFF + 4 * tx + k;
-                    float ic = USE_TMA ? iq[0] : __ldg(inv + (size_t)v * W + u);
-                    // pair (p, p+1): owner mask is the LEFT pixel (loss.py:285)
-                    if (u + 1 < W && msk[k]) {
-                        float a = fabsf(yc[0] - yc[1]) + fabsf(yc[BWD_CH] - yc[BWD_CH + 1]) + fabsf(yc[2 * BWD_CH] - yc[2 * BWD_CH + 1]);
-                        float w = expf(-exact::div3(a));
-                        float df = ic - (USE_TMA ? iq[1] : __ldg(inv + (size_t)v * W + u + 1));
-                        g += kx * w * (df > 0.f ? 1.f : (df < 0.f ? -1.f : 0.f));
-                    }
-                    if (u > 0 && (p.mask == nullptr || p.mask[(size_t)b * HW + (size_t)v * W + u - 1] != 0)) {
-                        float a = fabsf(yc[-1] - yc[0]) + fabsf(yc[BWD_CH - 1] - yc[BWD_CH]) + fabsf(yc[2 * BWD_CH - 1] - yc[2 * BWD_CH]);
-                        float w = expf(-exact::div3(a));
-                        float df = (USE_TMA ? iq[-1] : __ldg(inv + (size_t)v * W + u - 1)) - ic;
-                        g -= kx * w * (df > 0.f ? 1.f : (df < 0.f ? -1.f : 0.f));
-                    }
-                    if (v + 1 < H && msk[k]) {
-                        float a = fabsf(yc[0] - yc[PITCH]) + fabsf(yc[BWD_CH] - yc[BWD_CH + PITCH]) + fabsf(yc[2 * BWD_CH] - yc[2 * BWD_CH + PITCH]);
-                        float w = expf(-exact::div3(a));
-                        float df = ic - (USE_TMA ? iq[PITCH] : __ldg(inv + (size_t)(v + 1) * W + u));
-                        g += ky * w * (df > 0.f ? 1.f : (df < 0.f ? -1.f : 0.f));
-                    }
-                    if (v > 0 && (p.mask == nullptr || p.mask[(size_t)b * HW + (size_t)(v - 1) * W + u] != 0)) {
-                        float a = fabsf(yc[-PITCH] - yc[0]) + fabsf(yc[BWD_CH - PITCH] - yc[BWD_CH]) + fabsf(yc[2 * BWD_CH - PITCH] - yc[2 * BWD_CH]);
-                        float w = expf(-exact::div3(a));
-                        float df = (USE_TMA ? iq[-PITCH] : __ldg(inv + (size_t)(v - 1) * W + u)) - ic;
-                        g -= ky * w * (df > 0.f ? 1.f : (df < 0.f ? -1.f : 0.f));
-                    }
-                }
-                ginv[k] = g;
+                float wr = sW[(0 + k) * NT + tid], wd = sW[(5 + k) * NT + tid], wu = sW[(9 + k) * NT + tid];
+                float c = ic[k + 1];
+                float g = kx * (wr * sgn(c - ic[k + 2]) - wl * sgn(ic[k] - c)) + ky * (wd * sgn(c - id[k]) - wu * sgn(iu[k] - c));
+                ginv[k] = valid[k] ? mt + g : 0.f;
+                wl = wr;      // pair (q_k, q_k+1) is the left pair of output k+1 (same owner mask)
             }
         }
 #pragma unroll

@@ -265,6 +265,7 @@ __global__ void __launch_bounds__(NT, 2) fwd_kernel(const FwdParams p, const __g
             tma::mbar_wait(sBar + 1 + (i & 1), (i >> 1) & 1);
         }
         // ---- stage 1: warp both sources at every halo pixel ----
+        MGVS_PRAGMA_UNROLL_WARP
         for (int h = tid; h < FWD_ROWS * FWD_HALO_W; h += NT) {
             int hr = h / FWD_HALO_W, hc = h - hr * FWD_HALO_W;
             int pv = y0 - 1 + hr, pu = x0 - 1 + hc;
