@@ -10,6 +10,7 @@ from typing import Optional
 import torch
 
 from . import _lib
+from .sharding import allreduce_sums
 
 __all__ = ["LossConfig", "view_synthesis_loss", "launch_counter"]
 
@@ -122,9 +123,7 @@ class _ViewSynthesisLoss(torch.autograd.Function):
             launch_counter.n += FWD_LAUNCHES
             world = 1
             if cfg.process_group is not None:
-                import torch.distributed as dist
-                dist.all_reduce(sums, op=dist.ReduceOp.SUM, group=cfg.process_group)
-                world = dist.get_world_size(cfg.process_group)
+                world = allreduce_sums(sums, cfg.process_group)    # the only inter-GPU exchange of the path
             _lib.check(L.mgvs_finalize(ctypes.byref(prob), sums.data_ptr(), losses.data_ptr(), stream), "mgvs_finalize")
             launch_counter.n += FIN_LAUNCHES
         ctx.cfg = cfg
