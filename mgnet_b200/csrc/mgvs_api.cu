@@ -67,7 +67,7 @@ static bool tma_eligible(const MgvsProblem* p)
 // ---------------------------------------------------------------------------------------------
 // workspace layout (all offsets 256-byte aligned)
 struct Layout {
-    size_t cams, partials, imgsums, counter, pose_partials, total;
+    size_t cams, partials, imgsums, counter, pose_partials, packed[S], total;
     int tiles_x, tiles_y, tiles;
 };
 static inline size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
@@ -83,6 +83,9 @@ static Layout make_layout(int B, int H, int W, int n)
     L.imgsums = off; off = align256(off + sizeof(double) * (size_t)B * (4 * n + 3));
     L.counter = off; off = align256(off + 256);
     L.pose_partials = off; off = align256(off + sizeof(float) * (size_t)L.tiles * 24);
+    for (int s = 0; s < S; s++) {   // RGBA + 2-texel zero border copies of the sources
+        L.packed[s] = off; off = align256(off + sizeof(float4) * (size_t)B * (H + 2 * PACK_BORDER) * (W + 2 * PACK_BORDER));
+    }
     L.total = off;
     return L;
 }
@@ -135,6 +138,31 @@ __global__ void prep_kernel(int B, const float* __restrict__ camera, long long c
     }
     for (int k = 0; k < 6; k++) c.pad[k] = 0.f;
     cams[b] = c;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Re-lays both sources [B,3,H,W] out as RGBA float4 texels with a 2-texel zero border, [B][H+4][W+4]
+// (see mgvs_device.cuh "gather4").  Pure data movement: 24 B/px read, 32 B/px written.
+__global__ void __launch_bounds__(256) pack_sources_kernel(int B, int H, int W, const float* __restrict__ s0,
+                                                           const float* __restrict__ s1, float4* __restrict__ o0, float4* __restrict__ o1)
+{
+    const int Wp = W + 2 * PACK_BORDER, Hp = H + 2 * PACK_BORDER;
+    const long long total = (long long)B * Hp * Wp;
+    const int HW = H * W;
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+        int px = (int)(idx % Wp);
+        long long t = idx / Wp;
+        int py = (int)(t % Hp), b = (int)(t / Hp);
+        int x = px - PACK_BORDER, y = py - PACK_BORDER;
+        float4 a = make_float4(0.f, 0.f, 0.f, 0.f), c = a;
+        if (x >= 0 && x < W && y >= 0 && y < H) {
+            size_t base = (size_t)b * 3 * HW + (size_t)y * W + x;
+            a = make_float4(__ldg(s0 + base), __ldg(s0 + base + HW), __ldg(s0 + base + 2 * HW), 0.f);
+            c = make_float4(__ldg(s1 + base), __ldg(s1 + base + HW), __ldg(s1 + base + 2 * HW), 0.f);
+        }
+        o0[idx] = a;
+        o1[idx] = c;
+    }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -409,6 +437,12 @@ int mgvs_forward(const MgvsProblem* p, unsigned char* sel, double* sums, void* c
     fp.tgt = p->target; fp.src[0] = p->source[0]; fp.src[1] = p->source[1];
     for (int i = 0; i < p->n; i++) fp.inv[i] = p->inv_depth[i];
     fp.mask = p->mask; fp.cams = cams; fp.sel = sel;
+    fp.psrc[0] = (const float4*)(ws + L.packed[0]); fp.psrc[1] = (const float4*)(ws + L.packed[1]);
+    {
+        long long texels = (long long)p->B * (p->H + 2 * PACK_BORDER) * (p->W + 2 * PACK_BORDER);
+        int blocks = (int)((texels + 255) / 256 < 148 * 16 ? (texels + 255) / 256 : 148 * 16);
+        pack_sources_kernel<<<blocks, 256, 0, st>>>(p->B, p->H, p->W, p->source[0], p->source[1], (float4*)(ws + L.packed[0]), (float4*)(ws + L.packed[1]));
+    }
     fp.partials = (double*)(ws + L.partials);
     fp.alpha = p->ssim_weight; fp.oma = p->one_minus_ssim_weight;
     fp.tiles_x = L.tiles_x; fp.tiles_y = L.tiles_y;
@@ -460,6 +494,7 @@ int mgvs_backward(const MgvsProblem* p, const unsigned char* sel, const double* 
         bp.grad_inv[i] = grad_inv[i];
     }
     bp.mask = p->mask; bp.cams = (const Cam*)(ws + L.cams); bp.sel = sel; bp.sums = sums;
+    bp.psrc[0] = (const float4*)(ws + L.packed[0]); bp.psrc[1] = (const float4*)(ws + L.packed[1]);
     bp.imgsums = (const double*)(ws + L.imgsums); bp.g_losses = g_losses;
     bp.pose_partials = (float*)(ws + L.pose_partials);
     bp.alpha = p->ssim_weight; bp.oma = p->one_minus_ssim_weight;

@@ -26,6 +26,7 @@ struct BwdParams {
     const float* inv[MAXN];
     const unsigned char* mask;
     const Cam* cams;
+    const float4* psrc[S];        // packed RGBA + zero border copies of the sources (written by the forward)
     const unsigned char* sel;     // [n,B,H,W]
     const double* sums;           // [3n+3] global sums (N at [n], Nx at [3n+1], Ny at [3n+2])
     const double* imgsums;        // [B][4n+3] per-image sums from the forward (photo|smx|smy|invsum|N|Nx|Ny)
@@ -90,7 +91,7 @@ __device__ __forceinline__ void box_adjoint4(const float* __restrict__ mp, const
 }
 
 template <bool USE_TMA>
-__global__ void __launch_bounds__(NT, 2) bwd_kernel(const BwdParams p, const __grid_constant__ BwdMaps maps)
+__global__ void __launch_bounds__(NT, MIN_CTAS) bwd_kernel(const BwdParams p, const __grid_constant__ BwdMaps maps)
 {
     extern __shared__ __align__(128) float smem[];
     float* sY = smem;                               // [3][BWD_ROWS][PITCH]
@@ -111,7 +112,7 @@ __global__ void __launch_bounds__(NT, 2) bwd_kernel(const BwdParams p, const __g
     const int tyi = trem / p.tiles_x, txi = trem - tyi * p.tiles_x;
     const int x0 = txi * TW, y0 = tyi * TH;
     const int H = p.H, W = p.W, HW = H * W;
-    const int tx = tid & 15, ty = tid >> 4;
+    const int tx = tid % CG, ty = tid / CG;
     const int u0 = x0 + 4 * tx, v = y0 + ty;
 
     const bool border = (x0 == 0) || (y0 == 0) || (x0 + TW + 1 >= W) || (y0 + TH + 1 >= H);
@@ -159,8 +160,10 @@ __global__ void __launch_bounds__(NT, 2) bwd_kernel(const BwdParams p, const __g
     const float cf_ssim = Wp * p.alpha * (1.0f / 3.0f) * (-0.5f) * (1.0f / 9.0f);   // u/9 of App. B-3
     const float cf_l1 = Wp * p.oma * (1.0f / 3.0f);
 
-    const float* src0 = p.src[0] + (size_t)b * 3 * HW;
-    const float* src1 = p.src[1] + (size_t)b * 3 * HW;
+    const size_t pimg = (size_t)(H + 2 * PACK_BORDER) * (W + 2 * PACK_BORDER);
+    const float4* src0 = p.psrc[0] + (size_t)b * pimg;
+    const float4* src1 = p.psrc[1] + (size_t)b * pimg;
+    const int Wpk = W + 2 * PACK_BORDER;
 
     bool valid[4], msk[4];
     {
@@ -216,6 +219,19 @@ __global__ void __launch_bounds__(NT, 2) bwd_kernel(const BwdParams p, const __g
         }
     }
 
+    // bit it of pmask: my it-th stage-B pixel lies inside the image and its mask is true (scale independent)
+    unsigned pmask = 0;
+#pragma unroll
+    for (int it = 0; it < BWD_PIT; it++) {
+        int h = tid + it * NT;
+        if (h < BWD_PROWS * BWD_PW) {
+            int pr = h / BWD_PW, pc = h - pr * BWD_PW;
+            int pv = y0 - 1 + pr, pu = x0 - 1 + pc;
+            if (pv >= 0 && pv < H && pu >= 0 && pu < W && (p.mask == nullptr || p.mask[(size_t)b * HW + (size_t)pv * W + pu] != 0))
+                pmask |= 1u << it;
+        }
+    }
+
     float pacc[S][12];
 #pragma unroll
     for (int s = 0; s < S; s++)
@@ -235,55 +251,33 @@ __global__ void __launch_bounds__(NT, 2) bwd_kernel(const BwdParams p, const __g
             }
             tma::mbar_wait(sBar + 1 + (i & 1), (i >> 1) & 1);
         }
-        // ---- stage A: warp both sources on tile+2 ----
-        MGVS_PRAGMA_UNROLL_WARP
-        for (int h = tid; h < BWD_ROWS * BWD_W2; h += NT) {
-            int hr = h / BWD_W2, hc = h - hr * BWD_W2;
-            int pv = y0 - 2 + hr, pu = x0 - 2 + hc;
-            if (border) { pv = reflect_idx(pv, H); pu = reflect_idx(pu, W); }
-            float r[3], Xc[3];
-            exact::ray(Kinv, pu, pv, r);
-            float invv = USE_TMA ? sI[(pv - (y0 - 2)) * PITCH + (pu - (x0 - XOFF))] : __ldg(inv + pv * W + pu);
-            float d = exact::rcp_refined(fmaxf(invv, 1e-6f));
-#pragma unroll
-            for (int j = 0; j < 3; j++) Xc[j] = __fmul_rn(r[j], d);
-#pragma unroll
-            for (int s = 0; s < S; s++) {
-                exact::Proj pr;
-                exact::project(K, sCam + 18 + 12 * s, Xc, wm1, hm1, rw, rh, pr);
-                exact::Cell c;
-                exact::cell(pr.ix, pr.iy, H, W, c);
-                float wnw = __fmul_rn(c.wN, c.wW), wne = __fmul_rn(c.wN, c.wE), wsw = __fmul_rn(c.wS, c.wW),
-                      wse = __fmul_rn(c.wS, c.wE);
-                const float* sp = s == 0 ? src0 : src1;
-                float* dst = sX + s * 3 * BWD_CH + hr * PITCH + XOFF - 2 + hc;
-#pragma unroll
-                for (int ch = 0; ch < 3; ch++) {
-                    float vals[4];
-                    dst[ch * BWD_CH] = exact::blend(sp + ch * HW, W, c, wnw, wne, wsw, wse, vals);
-                }
-            }
-        }
-        // which source (0/1) is selected at each of my stage-B pixels; 2 = none
+        // which source (0/1) is selected at each of my stage-B pixels; 2 = none.  Loaded BEFORE stage A so
+        // the global-load latency hides behind the warp stage (the mask bits were fetched once per tile).
         unsigned char psel[BWD_PIT];
 #pragma unroll
         for (int it = 0; it < BWD_PIT; it++) {
-            int h = tid + it * NT;
             unsigned char code = 2;
-            if (h < BWD_PROWS * BWD_PW) {
+            if ((pmask >> it) & 1u) {
+                int h = tid + it * NT;
                 int pr = h / BWD_PW, pc = h - pr * BWD_PW;
-                int pv = y0 - 1 + pr, pu = x0 - 1 + pc;
-                if (pv >= 0 && pv < H && pu >= 0 && pu < W) {
-                    bool m = p.mask == nullptr || p.mask[(size_t)b * HW + (size_t)pv * W + pu] != 0;
-                    unsigned k = sel[(size_t)pv * W + pu];
-                    if (m) {
-                        if (p.automask) { if ((k & 1u) == 0) code = (unsigned char)(k >> 1); }
-                        else code = (unsigned char)k;
-                    }
-                }
+                unsigned k = sel[(size_t)(y0 - 1 + pr) * W + (x0 - 1 + pc)];
+                if (p.automask) { if ((k & 1u) == 0) code = (unsigned char)(k >> 1); }
+                else code = (unsigned char)k;
             }
             psel[it] = code;
         }
+        unsigned selq = 0;      // argmin codes of my 4 outputs (stage D)
+        if (v < H) {
+            const unsigned char* sq = sel + (size_t)v * W + u0;
+            if (u0 + 3 < W && ((W & 3) == 0)) selq = *reinterpret_cast<const unsigned*>(sq);
+            else {
+#pragma unroll
+                for (int k = 0; k < 4; k++) if (u0 + k < W) selq |= (unsigned)sq[k] << (8 * k);
+            }
+        }
+        // ---- stage A: warp both sources on tile+2 (software pipelined, mgvs_device.cuh) ----
+        warp_tile<2, BWD_ROWS, BWD_CH, USE_TMA>(sX, sX + 3 * BWD_CH, sI, inv, src0, src1, sCam, x0, y0, H, W, border,
+                                                 wm1, hm1, rw, rh, tid);
         __syncthreads();
 
         float G[S][3][4];
@@ -360,11 +354,6 @@ __global__ void __launch_bounds__(NT, 2) bwd_kernel(const BwdParams p, const __g
 
         // ---- stage D: per-output chain ----
         float ginv[4];
-        unsigned selq = 0;
-        if (v < H) {
-#pragma unroll
-            for (int k = 0; k < 4; k++) if (u0 + k < W) selq |= (unsigned)sel[(size_t)v * W + u0 + k] << (8 * k);
-        }
         // smoothness gradient (App. B-6): d/dinv of sum m*w*|inv_p - inv_q| / (N*c) plus the mean term
         {
             const float kx = sSm[i * 4 + 0], ky = sSm[i * 4 + 1], mt = sSm[i * 4 + 2];
@@ -401,7 +390,7 @@ __global__ void __launch_bounds__(NT, 2) bwd_kernel(const BwdParams p, const __g
 #pragma unroll
         for (int s = 0; s < S; s++) {
             const float* Rt = sCam + 18 + 12 * s;
-            const float* sp = s == 0 ? src0 : src1;
+            const float4* sp = s == 0 ? src0 : src1;
 #pragma unroll
             for (int k = 0; k < 4; k++) {
                 if (!valid[k]) continue;
@@ -426,18 +415,16 @@ __global__ void __launch_bounds__(NT, 2) bwd_kernel(const BwdParams p, const __g
                 for (int j = 0; j < 3; j++) Xc[j] = __fmul_rn(r[j], d);
                 exact::Proj pr;
                 exact::project(K, Rt, Xc, wm1, hm1, rw, rh, pr);
-                exact::Cell c;
-                exact::cell(pr.ix, pr.iy, H, W, c);
-                float gix = 0.f, giy = 0.f;
-                const float gch[3] = {g0, g1, g2};
-#pragma unroll
-                for (int ch = 0; ch < 3; ch++) {
-                    const float* pl = sp + ch * HW + c.off;
-                    float nw = c.nw ? __ldg(pl) : 0.f, ne = c.ne ? __ldg(pl + 1) : 0.f;
-                    float sw = c.sw ? __ldg(pl + W) : 0.f, se = c.se ? __ldg(pl + W + 1) : 0.f;
-                    gix += gch[ch] * ((ne - nw) * c.wN + (se - sw) * c.wS);
-                    giy += gch[ch] * ((sw - nw) * c.wW + (se - ne) * c.wE);
-                }
+                // bilinear adjoint (GridSampler backward w.r.t. the grid): out-of-image corners are zeros of the border
+                float xw = floorf(pr.ix), yn = floorf(pr.iy);
+                float wE = pr.ix - xw, wW = 1.0f - wE, wS = pr.iy - yn, wN = 1.0f - wS;
+                int cx0 = (int)fminf(fmaxf(xw, -2.0f), (float)W), cy0 = (int)fminf(fmaxf(yn, -2.0f), (float)H);
+                const float4* pc = sp + (cy0 + PACK_BORDER) * Wpk + (cx0 + PACK_BORDER);
+                float4 nw = __ldg(pc), ne = __ldg(pc + 1), sw = __ldg(pc + Wpk), se = __ldg(pc + Wpk + 1);
+                float gix = g0 * ((ne.x - nw.x) * wN + (se.x - sw.x) * wS) + g1 * ((ne.y - nw.y) * wN + (se.y - sw.y) * wS) +
+                            g2 * ((ne.z - nw.z) * wN + (se.z - sw.z) * wS);
+                float giy = g0 * ((sw.x - nw.x) * wW + (se.x - ne.x) * wE) + g1 * ((sw.y - nw.y) * wW + (se.y - ne.y) * wE) +
+                            g2 * ((sw.z - nw.z) * wW + (se.z - ne.z) * wE);
                 // projection adjoint (App. B-5)
                 float iz = exact::rcp_refined(pr.Z);
                 float gP0 = gix * iz, gP1 = giy * iz;

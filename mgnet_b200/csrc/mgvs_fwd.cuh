@@ -21,6 +21,7 @@ struct FwdParams {
     const float* inv[MAXN];
     const unsigned char* mask;   // may be null
     const Cam* cams;
+    const float4* psrc[S];       // packed RGBA + zero border copies of the sources (pack_sources_kernel)
     unsigned char* sel;          // may be null
     double* partials;            // [tiles][4n+3]
     float alpha, oma;
@@ -103,7 +104,7 @@ __device__ __forceinline__ void photometric4(const float* __restrict__ xs, const
 }
 
 template <bool USE_TMA>
-__global__ void __launch_bounds__(NT, 2) fwd_kernel(const FwdParams p, const __grid_constant__ FwdMaps maps)
+__global__ void __launch_bounds__(NT, MIN_CTAS) fwd_kernel(const FwdParams p, const __grid_constant__ FwdMaps maps)
 {
     extern __shared__ __align__(128) float smem[];
     float* sY = smem;
@@ -122,7 +123,7 @@ __global__ void __launch_bounds__(NT, 2) fwd_kernel(const FwdParams p, const __g
     const int tyi = trem / p.tiles_x, txi = trem - tyi * p.tiles_x;
     const int x0 = txi * TW, y0 = tyi * TH;
     const int H = p.H, W = p.W, HW = H * W;
-    const int tx = tid & 15, ty = tid >> 4;
+    const int tx = tid % CG, ty = tid / CG;
     const int u0 = x0 + 4 * tx, v = y0 + ty;     // this thread's 4 outputs: (v, u0..u0+3)
 
     const bool border = (x0 == 0) || (y0 == 0) || (x0 + TW >= W) || (y0 + TH >= H);
@@ -248,8 +249,9 @@ __global__ void __launch_bounds__(NT, 2) fwd_kernel(const FwdParams p, const __g
 
     const int nq = 4 * p.n + 3;
     double* my_partials = p.partials + (size_t)tile * nq;
-    const float* src0 = p.src[0] + (size_t)b * 3 * HW;
-    const float* src1 = p.src[1] + (size_t)b * 3 * HW;
+    const size_t pimg = (size_t)(H + 2 * PACK_BORDER) * (W + 2 * PACK_BORDER);
+    const float4* src0 = p.psrc[0] + (size_t)b * pimg;
+    const float4* src1 = p.psrc[1] + (size_t)b * pimg;
 
     for (int i = 0; i < p.n; i++) {
         const float* inv = p.inv[i] + (size_t)b * HW;
@@ -264,36 +266,9 @@ __global__ void __launch_bounds__(NT, 2) fwd_kernel(const FwdParams p, const __g
             }
             tma::mbar_wait(sBar + 1 + (i & 1), (i >> 1) & 1);
         }
-        // ---- stage 1: warp both sources at every halo pixel ----
-        MGVS_PRAGMA_UNROLL_WARP
-        for (int h = tid; h < FWD_ROWS * FWD_HALO_W; h += NT) {
-            int hr = h / FWD_HALO_W, hc = h - hr * FWD_HALO_W;
-            int pv = y0 - 1 + hr, pu = x0 - 1 + hc;
-            if (border) { pv = reflect_idx(pv, H); pu = reflect_idx(pu, W); }
-            float r[3], Xc[3];
-            exact::ray(Kinv, pu, pv, r);
-            // the reflected pixel lies inside the loaded box, so the zero-filled halo is never read
-            float invv = USE_TMA ? sI[(pv - (y0 - 1)) * PITCH + (pu - (x0 - XOFF))] : __ldg(inv + pv * W + pu);
-            float d = exact::rcp_refined(fmaxf(invv, 1e-6f));   // depth.py:15
-#pragma unroll
-            for (int j = 0; j < 3; j++) Xc[j] = __fmul_rn(r[j], d);
-#pragma unroll
-            for (int s = 0; s < S; s++) {
-                exact::Proj pr;
-                exact::project(K, sCam + 18 + 12 * s, Xc, wm1, hm1, rw, rh, pr);
-                exact::Cell c;
-                exact::cell(pr.ix, pr.iy, H, W, c);
-                float wnw = __fmul_rn(c.wN, c.wW), wne = __fmul_rn(c.wN, c.wE), wsw = __fmul_rn(c.wS, c.wW),
-                      wse = __fmul_rn(c.wS, c.wE);
-                const float* sp = s == 0 ? src0 : src1;
-                float* dst = sX + s * FWD_TILE3_FLOATS + hr * PITCH + XOFF - 1 + hc;
-#pragma unroll
-                for (int ch = 0; ch < 3; ch++) {
-                    float vals[4];
-                    dst[ch * FWD_CH] = exact::blend(sp + ch * HW, W, c, wnw, wne, wsw, wse, vals);
-                }
-            }
-        }
+        // ---- stage 1: warp both sources at every halo pixel (software pipelined, mgvs_device.cuh) ----
+        warp_tile<1, FWD_ROWS, FWD_CH, USE_TMA>(sX, sX + FWD_TILE3_FLOATS, sI, inv, src0, src1, sCam, x0, y0, H, W, border,
+                                                 wm1, hm1, rw, rh, tid);
         __syncthreads();
 
         // ---- stage 2: photometric maps, min/argmin, smoothness ----

@@ -23,7 +23,7 @@ class _Counter:
 
 
 launch_counter = _Counter()
-FWD_LAUNCHES = 3   # prep_kernel, fwd_kernel, reduce_kernel
+FWD_LAUNCHES = 4   # prep_kernel, pack_sources_kernel, fwd_kernel, reduce_kernel
 FIN_LAUNCHES = 1   # finalize_kernel
 BWD_LAUNCHES = 2   # bwd_kernel, pose_reduce_kernel
 
