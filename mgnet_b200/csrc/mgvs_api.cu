@@ -173,21 +173,17 @@ __global__ void __launch_bounds__(256) reduce_kernel(int B, int n, int tiles_per
                                                      const double* __restrict__ partials, double* __restrict__ imgsums,
                                                      unsigned int* __restrict__ counter, double* __restrict__ sums)
 {
-    __shared__ double sh[256];
     __shared__ bool last;
-    const int b = blockIdx.x, nq = 4 * n + 3, tid = threadIdx.x;
-    for (int q = 0; q < nq; q++) {
+    const int b = blockIdx.x, nq = 4 * n + 3, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    // one warp per quantity: lanes stride over the tiles of image b, then a fixed-order xor butterfly
+    for (int q = warp; q < nq; q += 8) {
         double acc = 0.0;
-        for (int t = tid; t < tiles_per_image; t += 256) acc += partials[((size_t)b * tiles_per_image + t) * nq + q];
-        sh[tid] = acc;
-        __syncthreads();
-        for (int o = 128; o > 0; o >>= 1) {
-            if (tid < o) sh[tid] += sh[tid + o];
-            __syncthreads();
-        }
-        if (tid == 0) imgsums[(size_t)b * nq + q] = sh[0];
-        __syncthreads();
+        for (int t = lane; t < tiles_per_image; t += 32) acc += partials[((size_t)b * tiles_per_image + t) * nq + q];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+        if (lane == 0) { imgsums[(size_t)b * nq + q] = acc; __threadfence(); }
     }
+    __syncthreads();
     if (tid == 0) {
         __threadfence();
         unsigned int done = atomicAdd(counter, 1u);

@@ -45,12 +45,12 @@ constexpr int BWD_CH = BWD_ROWS * PITCH;
 constexpr int BWD_W2 = TW + 4;                   // tile+2 halo width; smem col j <-> image col x0-XOFF+j
 constexpr int BWD_PROWS = TH + 2;                // tile+1 rows (coefficient maps)
 constexpr int BWD_PW = TW + 2;
-constexpr int BWD_MAP = BWD_PROWS * PITCH;       // one coefficient map; col j <-> image col x0-XOFF+j (like fwd)
+constexpr int BWD_MAP = BWD_PROWS * PITCH;       // coefficient texels per channel pass; col j <-> image col x0-XOFF+j (like fwd)
 constexpr int BWD_PIT = (BWD_PROWS * BWD_PW + NT - 1) / NT;   // stage-B iterations per thread
 constexpr int BWD_TILE3_FLOATS = (3 * BWD_CH + 31) / 32 * 32;
 constexpr int BWD_INV_FLOATS = (BWD_CH + 31) / 32 * 32;
 constexpr int BWD_NW = 13;                       // per-thread edge-aware weights kept across scales (see prologue)
-constexpr int BWD_SMEM_FLOATS = BWD_TILE3_FLOATS + S * 3 * BWD_CH + S * 3 * BWD_MAP + 2 * BWD_INV_FLOATS + BWD_NW * NT + 8 * 24 + 48 + 4 * MAXN + 8;
+constexpr int BWD_SMEM_FLOATS = BWD_TILE3_FLOATS + S * 3 * BWD_CH + 4 * BWD_MAP + 2 * BWD_INV_FLOATS + BWD_NW * NT + 8 * 24 + 48 + 4 * MAXN + 8;
 constexpr int BWD_SMEM_BYTES = BWD_SMEM_FLOATS * 4;
 
 __device__ __forceinline__ void bwd_load_tile(const float* __restrict__ img, float* __restrict__ dst, int x0, int y0,
@@ -66,28 +66,39 @@ __device__ __forceinline__ void bwd_load_tile(const float* __restrict__ img, flo
     }
 }
 
-// weighted 3x3 box adjoint of one coefficient map for 4 adjacent outputs (reflect-pad multiplicities);
-// the unweighted version is used by tiles that do not touch the image border
+// 3x3 box adjoint (reflect-pad multiplicities on border tiles) of the three coefficient maps of one channel
+// for 4 adjacent outputs, split by the source each tap belongs to.  One 128-bit smem load per tap brings
+// (a, b, c, [source==0]); out[s][m][k] = sum over the window of [source_p == s] * w_pq * coef_m(p).
 template <bool WEIGHTED>
-__device__ __forceinline__ void box_adjoint4(const float* __restrict__ mp, const float rwgt[3], const float (*cwgt)[3], float out[4])
+__device__ __forceinline__ void box_adjoint4(const float4* __restrict__ mp, const float rwgt[3], const float (*cwgt)[3],
+                                             float out[S][3][4])
 {
-    float col[6];
+    float col[S][3][6];
 #pragma unroll
     for (int dy = 0; dy < 3; dy++) {
-        const float* rr = mp + dy * PITCH;               // mp -> [map row of image row v-1][my output 0]
-        float4 a = *reinterpret_cast<const float4*>(rr);
-        float r6[6] = {rr[-1], a.x, a.y, a.z, a.w, rr[4]};
+        const float4* rr = mp + dy * PITCH;              // mp -> [map row of image row v-1][my output 0]
 #pragma unroll
         for (int j = 0; j < 6; j++) {
-            if (WEIGHTED) col[j] = dy == 0 ? rwgt[0] * r6[j] : fmaf(rwgt[dy], r6[j], col[j]);
-            else col[j] = dy == 0 ? r6[j] : col[j] + r6[j];
+            float4 t = rr[j - 1];
+            float m0 = WEIGHTED ? t.w * rwgt[dy] : t.w;
+            float m1 = WEIGHTED ? rwgt[dy] - m0 : 1.0f - t.w;
+            const float c3[3] = {t.x, t.y, t.z};
+#pragma unroll
+            for (int m = 0; m < 3; m++) {
+                col[0][m][j] = dy == 0 ? m0 * c3[m] : fmaf(m0, c3[m], col[0][m][j]);
+                col[1][m][j] = dy == 0 ? m1 * c3[m] : fmaf(m1, c3[m], col[1][m][j]);
+            }
         }
     }
 #pragma unroll
-    for (int k = 0; k < 4; k++) {
-        if (WEIGHTED) out[k] = cwgt[k][0] * col[k] + cwgt[k][1] * col[k + 1] + cwgt[k][2] * col[k + 2];
-        else out[k] = (col[k] + col[k + 1]) + col[k + 2];
-    }
+    for (int s = 0; s < S; s++)
+#pragma unroll
+        for (int m = 0; m < 3; m++)
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                if (WEIGHTED) out[s][m][k] = cwgt[k][0] * col[s][m][k] + cwgt[k][1] * col[s][m][k + 1] + cwgt[k][2] * col[s][m][k + 2];
+                else out[s][m][k] = (col[s][m][k] + col[s][m][k + 1]) + col[s][m][k + 2];
+            }
 }
 
 template <bool USE_TMA>
@@ -96,8 +107,9 @@ __global__ void __launch_bounds__(NT, MIN_CTAS) bwd_kernel(const BwdParams p, co
     extern __shared__ __align__(128) float smem[];
     float* sY = smem;                               // [3][BWD_ROWS][PITCH]
     float* sX = sY + BWD_TILE3_FLOATS;              // [S][3][BWD_ROWS][PITCH]
-    float* sCo = sX + S * 3 * BWD_CH;               // [S][3 maps][BWD_PROWS][PITCH]  (one channel at a time)
-    float* sInv = sCo + S * 3 * BWD_MAP;            // [2][BWD_ROWS][PITCH] inverse-depth ring (TMA path)
+    float4* sCo = reinterpret_cast<float4*>(sX + S * 3 * BWD_CH);   // [BWD_PROWS][PITCH] texels (a, b, c, [source==0]) of
+                                                                    // the current channel: one 128-bit load per tap
+    float* sInv = sX + S * 3 * BWD_CH + 4 * BWD_MAP; // [2][BWD_ROWS][PITCH] inverse-depth ring (TMA path)
     float* sW = sInv + 2 * BWD_INV_FLOATS;          // [13][NT] masked smoothness weights of my 4 outputs
     float* sRed = sW + BWD_NW * NT;                 // [8 warps][24]
     float* sCam = sRed + 8 * 24;                    // 48
@@ -324,30 +336,24 @@ __global__ void __launch_bounds__(NT, MIN_CTAS) bwd_kernel(const BwdParams p, co
                             cc = cf_ssim * ds_dexy;
                         }
                     }
-                    float* m0 = sCo + pr * PITCH + XOFF - 1 + pc;        // set 0
-                    float* m1 = m0 + 3 * BWD_MAP;                        // set 1
-                    bool s0 = (s == 0), s1 = (s == 1);
-                    m0[0] = s0 ? ca : 0.f; m0[BWD_MAP] = s0 ? cb : 0.f; m0[2 * BWD_MAP] = s0 ? cc : 0.f;
-                    m1[0] = s1 ? ca : 0.f; m1[BWD_MAP] = s1 ? cb : 0.f; m1[2 * BWD_MAP] = s1 ? cc : 0.f;
+                    sCo[pr * PITCH + XOFF - 1 + pc] = make_float4(ca, cb, cc, s == 0 ? 1.f : 0.f);   // zeros when unselected
                 }
             }
             __syncthreads();
             // ---- stage C: 3x3 box adjoint (with reflect-pad multiplicities on border tiles) for my 4 outputs ----
+            {
+                float box[S][3][4];
+                const float4* mp = sCo + ty * PITCH + XOFF + 4 * tx;
+                if (border) box_adjoint4<true>(mp, rwgt, cwgt, box);
+                else box_adjoint4<false>(mp, rwgt, cwgt, box);
 #pragma unroll
-            for (int s = 0; s < S; s++) {
-                float box[3][4];
+                for (int s = 0; s < S; s++)
 #pragma unroll
-                for (int m = 0; m < 3; m++) {
-                    const float* mp = sCo + (s * 3 + m) * BWD_MAP + ty * PITCH + XOFF + 4 * tx;
-                    if (border) box_adjoint4<true>(mp, rwgt, cwgt, box[m]);
-                    else box_adjoint4<false>(mp, rwgt, cwgt, box[m]);
-                }
-#pragma unroll
-                for (int k = 0; k < 4; k++) {
-                    float xq = sX[s * 3 * BWD_CH + ch * BWD_CH + (ty + 2) * PITCH + XOFF + 4 * tx + k];
-                    float yq = sY[ch * BWD_CH + (ty + 2) * PITCH + XOFF + 4 * tx + k];
-                    G[s][ch][k] = box[0][k] + xq * box[1][k] + yq * box[2][k];
-                }
+                    for (int k = 0; k < 4; k++) {
+                        float xq = sX[s * 3 * BWD_CH + ch * BWD_CH + (ty + 2) * PITCH + XOFF + 4 * tx + k];
+                        float yq = sY[ch * BWD_CH + (ty + 2) * PITCH + XOFF + 4 * tx + k];
+                        G[s][ch][k] = box[s][0][k] + xq * box[s][1][k] + yq * box[s][2][k];
+                    }
             }
             __syncthreads();   // maps free for the next channel
         }
