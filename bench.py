@@ -268,8 +268,7 @@ def main():
                       tk["camera_matrix"], pk["poses"].detach(), tk.get("reprojection_mask"), ws)
         a, b_, c = (torch.cuda.Event(enable_timing=True) for _ in range(3))
         a.record()
-        _lib.check(L.mgvs_forward(ctypes.byref(prob), sel.data_ptr(), sums.data_ptr(), stream))
-        _lib.check(L.mgvs_finalize(ctypes.byref(prob), sums.data_ptr(), losses.data_ptr(), stream))
+        _lib.check(L.mgvs_forward_losses(ctypes.byref(prob), sel.data_ptr(), sums.data_ptr(), losses.data_ptr(), stream))
         b_.record()
         _lib.check(L.mgvs_backward(ctypes.byref(prob), sel.data_ptr(), sums.data_ptr(), g.data_ptr(), arr, gp.data_ptr(), stream))
         c.record()

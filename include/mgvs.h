@@ -85,6 +85,10 @@ int mgvs_num_sums(int n);
  *   sums [3n+3] double out: this rank's partial sums (see above). */
 int mgvs_forward(const MgvsProblem *p, unsigned char *sel, double *sums, void *cuda_stream);
 
+/* Single-rank convenience: mgvs_forward followed by mgvs_finalize in the same launches (the last block of the
+ * reduction also writes the two losses).  losses [2] float out; NULL behaves exactly like mgvs_forward. */
+int mgvs_forward_losses(const MgvsProblem *p, unsigned char *sel, double *sums, float *losses, void *cuda_stream);
+
 /* Turns (globally reduced) sums into the two weighted scalars of loss.py:151-154.
  *   losses [2] float out: loss_photometric, loss_smoothness. */
 int mgvs_finalize(const MgvsProblem *p, const double *sums, float *losses, void *cuda_stream);

@@ -98,6 +98,8 @@ def lib():
     L.mgvs_workspace_bytes.argtypes = [ci, ci, ci, ci]
     L.mgvs_forward.restype = ci
     L.mgvs_forward.argtypes = [PP, vp, vp, vp]
+    L.mgvs_forward_losses.restype = ci
+    L.mgvs_forward_losses.argtypes = [PP, vp, vp, vp, vp]
     L.mgvs_finalize.restype = ci
     L.mgvs_finalize.argtypes = [PP, vp, vp, vp]
     L.mgvs_backward.restype = ci
@@ -117,7 +119,7 @@ def lib():
 
 
 EXPORTED_SYMBOLS = (
-    "mgvs_abi_version", "mgvs_last_error", "mgvs_num_sums", "mgvs_workspace_bytes", "mgvs_forward",
+    "mgvs_abi_version", "mgvs_last_error", "mgvs_num_sums", "mgvs_workspace_bytes", "mgvs_forward", "mgvs_forward_losses",
     "mgvs_finalize", "mgvs_backward", "mgvs_view_synthesis", "mgvs_reconstruct", "mgvs_project", "mgvs_test_div",
 )
 

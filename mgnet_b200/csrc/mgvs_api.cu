@@ -94,11 +94,9 @@ static Layout make_layout(int B, int H, int W, int n)
 // Camera table: K, Kinv (camera.py:72-81) and R|t per source (pose_utils.py:9-51, pose.py:41-47).
 // sin/cos are the correctly rounded fp32 values (fp64 evaluation); the two tiny bmm's of euler2mat
 // round like ATen's small-matrix path: acc = 0; acc += a*b with separately rounded mul and add.
-__global__ void prep_kernel(int B, const float* __restrict__ camera, long long cbs, long long crs,
-                            const float* __restrict__ poses, Cam* __restrict__ cams)
+__device__ __forceinline__ void prep_one(int b, const float* __restrict__ camera, long long cbs, long long crs,
+                                         const float* __restrict__ poses, Cam* __restrict__ cams)
 {
-    int b = blockIdx.x * blockDim.x + threadIdx.x;
-    if (b >= B) return;
     Cam c;
     for (int r = 0; r < 3; r++)
         for (int k = 0; k < 3; k++) c.K[r * 3 + k] = camera[b * cbs + r * crs + k];
@@ -143,13 +141,21 @@ __global__ void prep_kernel(int B, const float* __restrict__ camera, long long c
 // ---------------------------------------------------------------------------------------------
 // Re-lays both sources [B,3,H,W] out as RGBA float4 texels with a 2-texel zero border, [B][H+4][W+4]
 // (see mgvs_device.cuh "gather4").  Pure data movement: 24 B/px read, 32 B/px written.
+// The last block of the grid does not pack: it writes the per-image camera table instead (what used to be a
+// separate 1-block prep_kernel launch).
 __global__ void __launch_bounds__(256) pack_sources_kernel(int B, int H, int W, const float* __restrict__ s0,
-                                                           const float* __restrict__ s1, float4* __restrict__ o0, float4* __restrict__ o1)
+                                                           const float* __restrict__ s1, float4* __restrict__ o0, float4* __restrict__ o1,
+                                                           const float* __restrict__ camera, long long cbs, long long crs,
+                                                           const float* __restrict__ poses, Cam* __restrict__ cams)
 {
+    if (blockIdx.x == gridDim.x - 1) {
+        for (int b = threadIdx.x; b < B; b += blockDim.x) prep_one(b, camera, cbs, crs, poses, cams);
+        return;
+    }
     const int Wp = W + 2 * PACK_BORDER, Hp = H + 2 * PACK_BORDER;
     const long long total = (long long)B * Hp * Wp;
     const int HW = H * W;
-    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)(gridDim.x - 1) * blockDim.x) {
         int px = (int)(idx % Wp);
         long long t = idx / Wp;
         int py = (int)(t % Hp), b = (int)(t / Hp);
@@ -169,11 +175,25 @@ __global__ void __launch_bounds__(256) pack_sources_kernel(int B, int H, int W, 
 // Fixed-order reduction of the per-tile partial sums: one CTA per image, then the last CTA to finish
 // folds the per-image sums (smoothness normalised by the per-image mean, depth.py:48-51) into the
 // rank-level vector [3n+3].
+__device__ __forceinline__ void losses_from_sums_dev(int n, const double* sums, float photo_w, float smooth_w, float* losses)
+{   // loss.py:151-154, 252-254, 274-294
+    double N = sums[n], Nx = sums[3 * n + 1], Ny = sums[3 * n + 2];
+    double lp = 0.0, ls = 0.0;
+    for (int i = 0; i < n; i++) {
+        lp += sums[i] / N;
+        ls += (sums[n + 1 + i] / Nx + sums[2 * n + 1 + i] / Ny) / (double)(1 << i);
+    }
+    losses[0] = (float)(lp / (double)n * (double)photo_w);
+    losses[1] = (float)(ls / (double)n * (double)smooth_w);
+}
+
 __global__ void __launch_bounds__(256) reduce_kernel(int B, int n, int tiles_per_image, long long HW,
                                                      const double* __restrict__ partials, double* __restrict__ imgsums,
-                                                     unsigned int* __restrict__ counter, double* __restrict__ sums)
+                                                     unsigned int* __restrict__ counter, double* __restrict__ sums,
+                                                     float photo_w, float smooth_w, float* __restrict__ losses /* may be null */)
 {
     __shared__ bool last;
+    __shared__ double sh_sums[3 * MAXN + 3];
     const int b = blockIdx.x, nq = 4 * n + 3, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     // one warp per quantity: lanes stride over the tiles of image b, then a fixed-order xor butterfly
     for (int q = warp; q < nq; q += 8) {
@@ -192,36 +212,35 @@ __global__ void __launch_bounds__(256) reduce_kernel(int B, int n, int tiles_per
     __syncthreads();
     if (!last) return;
     __threadfence();
-    if (tid < 3 * n + 3) {
+    // last CTA: fold the per-image sums (one warp per output quantity, lanes over images, fixed order)
+    for (int q = warp; q < 3 * n + 3; q += 8) {
         double acc = 0.0;
-        for (int bb = 0; bb < B; bb++) {
-            const volatile double* is = imgsums + (size_t)bb * nq;
-            if (tid < n) acc += is[tid];                                    // photometric sums
-            else if (tid == n) acc += is[4 * n];                            // N
-            else if (tid < 3 * n + 1) {                                     // smoothness x / y
-                int which = (tid - n - 1) / n, i = (tid - n - 1) % n;
-                double mean = is[3 * n + i] / (double)HW;
+        for (int bb = lane; bb < B; bb += 32) {
+            const double* is = imgsums + (size_t)bb * nq;
+            if (q < n) acc += __ldcg(is + q);                                   // photometric sums
+            else if (q == n) acc += __ldcg(is + 4 * n);                         // N
+            else if (q < 3 * n + 1) {                                           // smoothness x / y
+                int which = (q - n - 1) / n, i = (q - n - 1) % n;
+                double mean = __ldcg(is + 3 * n + i) / (double)HW;
                 double c = mean < 1e-6 ? 1e-6 : mean;
-                acc += is[(1 + which) * n + i] / c;
-            } else acc += is[4 * n + 1 + (tid - 3 * n - 1)];                // Nx, Ny
+                acc += __ldcg(is + (1 + which) * n + i) / c;
+            } else acc += __ldcg(is + 4 * n + 1 + (q - 3 * n - 1));             // Nx, Ny
         }
-        sums[tid] = acc;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+        if (lane == 0) { sums[q] = acc; sh_sums[q] = acc; }
+    }
+    if (losses != nullptr) {      // single-rank call: no all-reduce in between, finish here
+        __syncthreads();
+        if (tid == 0) losses_from_sums_dev(n, sh_sums, photo_w, smooth_w, losses);
     }
 }
 
-// loss.py:151-154, 252-254, 274-294
 __global__ void finalize_kernel(int n, const double* __restrict__ sums, float photo_w, float smooth_w,
                                 float* __restrict__ losses)
 {
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
-    double N = sums[n], Nx = sums[3 * n + 1], Ny = sums[3 * n + 2];
-    double lp = 0.0, ls = 0.0;
-    for (int i = 0; i < n; i++) {
-        lp += sums[i] / N;
-        ls += (sums[n + 1 + i] / Nx + sums[2 * n + 1 + i] / Ny) / (double)(1 << i);
-    }
-    losses[0] = (float)(lp / (double)n * (double)photo_w);
-    losses[1] = (float)(ls / (double)n * (double)smooth_w);
+    losses_from_sums_dev(n, sums, photo_w, smooth_w, losses);
 }
 
 // Pose gradient: fixed-order sum of the per-tile partials of dL/d(R|t), then the Euler chain through
@@ -416,7 +435,7 @@ size_t mgvs_workspace_bytes(int B, int H, int W, int n)
     return make_layout(B, H, W, n).total;
 }
 
-int mgvs_forward(const MgvsProblem* p, unsigned char* sel, double* sums, void* cuda_stream)
+int mgvs_forward_losses(const MgvsProblem* p, unsigned char* sel, double* sums, float* losses, void* cuda_stream)
 {
     int rc = check_problem(p);
     if (rc) return rc;
@@ -426,7 +445,6 @@ int mgvs_forward(const MgvsProblem* p, unsigned char* sel, double* sums, void* c
     char* ws = (char*)p->workspace;
     Cam* cams = (Cam*)(ws + L.cams);
     cudaMemsetAsync(ws + L.counter, 0, 256, st);   // arrival counter of reduce_kernel (workspace arrives uninitialised)
-    prep_kernel<<<(p->B + 63) / 64, 64, 0, st>>>(p->B, p->camera, p->cam_batch_stride, p->cam_row_stride, p->poses, cams);
     FwdParams fp;
     memset(&fp, 0, sizeof(fp));
     fp.B = p->B; fp.H = p->H; fp.W = p->W; fp.n = p->n; fp.automask = p->automask;
@@ -437,7 +455,8 @@ int mgvs_forward(const MgvsProblem* p, unsigned char* sel, double* sums, void* c
     {
         long long texels = (long long)p->B * (p->H + 2 * PACK_BORDER) * (p->W + 2 * PACK_BORDER);
         int blocks = (int)((texels + 255) / 256 < 148 * 16 ? (texels + 255) / 256 : 148 * 16);
-        pack_sources_kernel<<<blocks, 256, 0, st>>>(p->B, p->H, p->W, p->source[0], p->source[1], (float4*)(ws + L.packed[0]), (float4*)(ws + L.packed[1]));
+        pack_sources_kernel<<<blocks + 1, 256, 0, st>>>(p->B, p->H, p->W, p->source[0], p->source[1], (float4*)(ws + L.packed[0]),
+                                                        (float4*)(ws + L.packed[1]), p->camera, p->cam_batch_stride, p->cam_row_stride, p->poses, cams);
     }
     fp.partials = (double*)(ws + L.partials);
     fp.alpha = p->ssim_weight; fp.oma = p->one_minus_ssim_weight;
@@ -459,8 +478,14 @@ int mgvs_forward(const MgvsProblem* p, unsigned char* sel, double* sums, void* c
         fwd_kernel<false><<<L.tiles, NT, FWD_SMEM_BYTES, st>>>(fp, maps);
     }
     reduce_kernel<<<p->B, 256, 0, st>>>(p->B, p->n, L.tiles_x * L.tiles_y, (long long)p->H * p->W, fp.partials,
-                                        (double*)(ws + L.imgsums), (unsigned int*)(ws + L.counter), sums);
+                                        (double*)(ws + L.imgsums), (unsigned int*)(ws + L.counter), sums,
+                                        p->photometric_weight, p->smoothing_weight, losses);
     return check_launch("mgvs_forward");
+}
+
+int mgvs_forward(const MgvsProblem* p, unsigned char* sel, double* sums, void* cuda_stream)
+{
+    return mgvs_forward_losses(p, sel, sums, nullptr, cuda_stream);
 }
 
 int mgvs_finalize(const MgvsProblem* p, const double* sums, float* losses, void* cuda_stream)

@@ -23,7 +23,7 @@ class _Counter:
 
 
 launch_counter = _Counter()
-FWD_LAUNCHES = 4   # prep_kernel, pack_sources_kernel, fwd_kernel, reduce_kernel
+FWD_LAUNCHES = 3   # pack_sources_kernel (+camera table), fwd_kernel, reduce_kernel
 FIN_LAUNCHES = 1   # finalize_kernel
 BWD_LAUNCHES = 2   # bwd_kernel, pose_reduce_kernel
 
@@ -119,13 +119,18 @@ class _ViewSynthesisLoss(torch.autograd.Function):
             prob = _lib.MgvsProblem()
             _fill_problem(prob, cfg, tgt, prev, nxt, inv, camera, poses, mask, ws)
             stream = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
-            _lib.check(L.mgvs_forward(ctypes.byref(prob), sel.data_ptr(), sums.data_ptr(), stream), "mgvs_forward")
-            launch_counter.n += FWD_LAUNCHES
             world = 1
-            if cfg.process_group is not None:
+            if cfg.process_group is None:
+                # single rank: the reduction's last block also writes the two losses (no finalize launch)
+                _lib.check(L.mgvs_forward_losses(ctypes.byref(prob), sel.data_ptr(), sums.data_ptr(), losses.data_ptr(), stream),
+                           "mgvs_forward_losses")
+                launch_counter.n += FWD_LAUNCHES
+            else:
+                _lib.check(L.mgvs_forward(ctypes.byref(prob), sel.data_ptr(), sums.data_ptr(), stream), "mgvs_forward")
+                launch_counter.n += FWD_LAUNCHES
                 world = allreduce_sums(sums, cfg.process_group)    # the only inter-GPU exchange of the path
-            _lib.check(L.mgvs_finalize(ctypes.byref(prob), sums.data_ptr(), losses.data_ptr(), stream), "mgvs_finalize")
-            launch_counter.n += FIN_LAUNCHES
+                _lib.check(L.mgvs_finalize(ctypes.byref(prob), sums.data_ptr(), losses.data_ptr(), stream), "mgvs_finalize")
+                launch_counter.n += FIN_LAUNCHES
         ctx.cfg = cfg
         ctx.n = n
         ctx.has_mask = mask is not None

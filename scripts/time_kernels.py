@@ -27,7 +27,7 @@ for name in names:
         p, t = sets[it % 3]
         prob = _lib.MgvsProblem(); _fill_problem(prob, cfg, t["image_orig"], t["image_prev_orig"], t["image_next_orig"], p["depth"], t["camera_matrix"], p["poses"], t.get("reprojection_mask"), ws)
         a, b, c = (torch.cuda.Event(enable_timing=True) for _ in range(3))
-        a.record(); _lib.check(L.mgvs_forward(ctypes.byref(prob), sel.data_ptr(), sums.data_ptr(), st)); _lib.check(L.mgvs_finalize(ctypes.byref(prob), sums.data_ptr(), losses.data_ptr(), st)); b.record()
+        a.record(); _lib.check(L.mgvs_forward_losses(ctypes.byref(prob), sel.data_ptr(), sums.data_ptr(), losses.data_ptr(), st)); b.record()
         _lib.check(L.mgvs_backward(ctypes.byref(prob), sel.data_ptr(), sums.data_ptr(), g.data_ptr(), arr, gp.data_ptr(), st)); c.record(); torch.cuda.synchronize()
         if it >= 3: tf.append(a.elapsed_time(b)); tb.append(b.elapsed_time(c))
     f, bb = statistics.median(tf), statistics.median(tb)
