@@ -153,6 +153,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--e2e-images", default="uint8", choices=["uint8", "float32"],
+                    help="dtype of the host images of the e2e leg (uint8 = what the reference's data loader produces)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
 
@@ -299,36 +301,52 @@ def main():
     if not args.no_e2e:
         def pin(x):
             return x.pin_memory()
+        from mgnet_b200.synthetic import quantize_images
         host = []
         for pred, tgt in sets_host:
+            if args.e2e_images == "uint8":      # what the reference's data loader hands over (mg_net.py:320-335)
+                tgt = quantize_images(tgt)[0]
             host.append(({"depth": [pin(d) for d in pred["depth"]], "poses": pin(pred["poses"])}, {kk: pin(v) for kk, v in tgt.items()}))
         h2d = sum(d.numel() * d.element_size() for d in host[0][0]["depth"]) + host[0][0]["poses"].numel() * 4 + \
             sum(v.numel() * v.element_size() for v in host[0][1].values())
         copy_stream = torch.cuda.Stream(dev)
         out_host = torch.empty(2, dtype=torch.float32).pin_memory()
-        slots = [None, None]
+
+        # two persistent device-side input slots (double buffer): no allocator traffic inside the timed region
+        class Slot:
+            def __init__(self, hp_, ht_):
+                self.pd = {"depth": [torch.empty_like(d, device=dev).requires_grad_(True) for d in hp_["depth"]],
+                           "poses": torch.empty_like(hp_["poses"], device=dev).requires_grad_(True)}
+                self.td = {kk: torch.empty_like(v, device=dev) for kk, v in ht_.items()}
+                self.ready = torch.cuda.Event()
+                self.free = torch.cuda.Event()
+                self.free.record(torch.cuda.current_stream(dev))
+        slots = [Slot(*host[0]), Slot(*host[0])]
 
         def upload(k):
             hp_, ht_ = host[k % nsets]
-            with torch.cuda.stream(copy_stream):
-                pd = {"depth": [d.to(dev, non_blocking=True) for d in hp_["depth"]], "poses": hp_["poses"].to(dev, non_blocking=True)}
-                td = {kk: v.to(dev, non_blocking=True) for kk, v in ht_.items()}
-                ev = torch.cuda.Event()
-                ev.record(copy_stream)
-            slots[k % 2] = (pd, td, ev)
+            sl = slots[k % 2]
+            with torch.cuda.stream(copy_stream), torch.no_grad():
+                copy_stream.wait_event(sl.free)          # the step that last read this slot has finished
+                for dst, src in zip(sl.pd["depth"], hp_["depth"]):
+                    dst.copy_(src, non_blocking=True)
+                sl.pd["poses"].copy_(hp_["poses"], non_blocking=True)
+                for kk, v in ht_.items():
+                    sl.td[kk].copy_(v, non_blocking=True)
+                sl.ready.record(copy_stream)
 
         def e2e_step(k, last):
-            pd, td, ev = slots[k % 2]
-            torch.cuda.current_stream(dev).wait_event(ev)
+            sl = slots[k % 2]
+            cur = torch.cuda.current_stream(dev)
+            cur.wait_event(sl.ready)
             if not last:
                 upload(k + 1)      # prefetch the next step's inputs while this step computes
-            for x in pd["depth"] + [pd["poses"]]:
-                x.requires_grad_(True)
-            out = mod(pd, td)
+            for x in sl.pd["depth"] + [sl.pd["poses"]]:
+                x.grad = None
+            out = mod(sl.pd, sl.td)
             (out["loss_photometric"] + out["loss_smoothness"]).backward()
             out_host.copy_(torch.stack([out["loss_photometric"].detach(), out["loss_smoothness"].detach()]), non_blocking=True)
-            for tns in pd["depth"] + [pd["poses"]] + list(td.values()):
-                tns.record_stream(torch.cuda.current_stream(dev))
+            sl.free.record(cur)
 
         upload(0)
         for k in range(args.warmup):
@@ -350,7 +368,9 @@ def main():
         ms_e = float(te.item()) / args.steps
         e2e = {"value": px_step / (ms_e * 1e-3) / 1e9, "unit": "Gpixel/s", "h2d_bytes_per_step": int(h2d),
                "d2h_bytes_per_step": 8, "ms_per_step": ms_e, "wall_ms_per_step": wall_ms / args.steps,
-               "note": "pinned host inputs, H2D of step k+1 overlapped with compute of step k on a copy stream"}
+               "images": args.e2e_images,
+               "note": "pinned host inputs (images as %s, inverse depth fp32), H2D of step k+1 overlapped with compute of step k on a copy stream" % (
+                   "the data loader's uint8, converted in-kernel like the reference's x.float()/255" if args.e2e_images == "uint8" else "float32")}
 
     clocks = sampler.stop() if rank == 0 else None
 

@@ -23,9 +23,11 @@
 extern "C" {
 #endif
 
-#define MGVS_ABI_VERSION 1
+#define MGVS_ABI_VERSION 2
 #define MGVS_MAX_SCALES 8   /* n: number of inverse-depth maps (reference: 3, mg_net.py:760-764) */
 #define MGVS_NUM_SOURCES 2  /* S: prev, next -- hard-coded in the reference (loss.py:116) */
+
+enum { MGVS_IMAGE_F32 = 0, MGVS_IMAGE_U8 = 1 };
 
 enum {
     MGVS_OK = 0,
@@ -38,8 +40,9 @@ enum {
 /* One problem instance == one call of MultiViewPhotometricLoss.forward (loss.py:111-154). */
 typedef struct MgvsProblem {
     int B, H, W, n;
-    const float *target;                      /* targets["image_orig"]       [B,3,H,W]  (loss.py:125) */
-    const float *source[MGVS_NUM_SOURCES];    /* image_prev_orig, image_next_orig       (loss.py:116) */
+    const void *target;                       /* targets["image_orig"]       [B,3,H,W]  (loss.py:125);
+                                                 float, or uint8 when image_dtype == MGVS_IMAGE_U8 */
+    const void *source[MGVS_NUM_SOURCES];     /* image_prev_orig, image_next_orig       (loss.py:116) */
     const float *inv_depth[MGVS_MAX_SCALES];  /* predictions["depth"][i]     [B,1,H,W]  (loss.py:112) */
     const float *camera;                      /* targets["camera_matrix"]; element (b,r,c) at
                                                  camera[b*cam_batch_stride + r*cam_row_stride + c];
@@ -60,6 +63,11 @@ typedef struct MgvsProblem {
     void *workspace;            /* >= mgvs_workspace_bytes(B,H,W,n) bytes, 256-byte aligned; must stay
                                    untouched between mgvs_forward and the matching mgvs_backward */
     size_t workspace_bytes;
+    int image_dtype;            /* MGVS_IMAGE_F32: the three images are float in [0,1] (what the loss receives in the
+                                   reference).  MGVS_IMAGE_U8: they are the uint8 images the data loader produced and
+                                   the library applies the caller's own conversion `x.float() / 255.0`
+                                   (mg_net.py:320-335) on the fly -- one correctly rounded division, so every
+                                   result is bit-identical to the float path; host->device traffic drops 4x. */
 } MgvsProblem;
 
 int mgvs_abi_version(void);
@@ -67,6 +75,8 @@ const char *mgvs_last_error(void);
 
 /* Scratch the caller must provide (per-tile partial sums, camera table, pose-gradient partials). */
 size_t mgvs_workspace_bytes(int B, int H, int W, int n);
+/* Same for a given image_dtype (uint8 ingestion keeps float copies of the three images in the workspace). */
+size_t mgvs_workspace_bytes_ex(int B, int H, int W, int n, int image_dtype);
 
 /* Number of doubles in the partial-sum vector: 3n+3 =
  *   [0,n)     sum over masked pixels of the per-pixel minimum photometric loss, per scale (loss.py:245)

@@ -15,6 +15,8 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _CSRC = os.path.join(_HERE, "csrc")
 LIB_PATH = os.environ.get("MGVS_LIB_PATH") or os.path.join(_HERE, "libmgvs.so")   # override: kernel-variant experiments only
 MAX_SCALES = 8
+ABI_VERSION = 2
+IMAGE_F32, IMAGE_U8 = 0, 1
 NUM_SOURCES = 2
 
 NVCC_FLAGS = [
@@ -37,6 +39,7 @@ class MgvsProblem(ctypes.Structure):
         ("photometric_weight", ctypes.c_float), ("smoothing_weight", ctypes.c_float),
         ("automask", ctypes.c_int), ("reduce_op", ctypes.c_int), ("padding_mode", ctypes.c_int),
         ("workspace", ctypes.c_void_p), ("workspace_bytes", ctypes.c_size_t),
+        ("image_dtype", ctypes.c_int),
     ]
 
 
@@ -96,6 +99,8 @@ def lib():
     L.mgvs_num_sums.argtypes = [ci]
     L.mgvs_workspace_bytes.restype = ctypes.c_size_t
     L.mgvs_workspace_bytes.argtypes = [ci, ci, ci, ci]
+    L.mgvs_workspace_bytes_ex.restype = ctypes.c_size_t
+    L.mgvs_workspace_bytes_ex.argtypes = [ci, ci, ci, ci, ci]
     L.mgvs_forward.restype = ci
     L.mgvs_forward.argtypes = [PP, vp, vp, vp]
     L.mgvs_forward_losses.restype = ci
@@ -112,14 +117,14 @@ def lib():
     L.mgvs_project.argtypes = [ci, ci, ci, vp, vp, ll, ll, vp, vp, vp]
     L.mgvs_test_div.restype = ci
     L.mgvs_test_div.argtypes = [vp, vp, vp, ll, vp]
-    if L.mgvs_abi_version() != 1:
+    if L.mgvs_abi_version() != ABI_VERSION:
         raise RuntimeError("libmgvs.so ABI version mismatch")
     _lib = L
     return L
 
 
 EXPORTED_SYMBOLS = (
-    "mgvs_abi_version", "mgvs_last_error", "mgvs_num_sums", "mgvs_workspace_bytes", "mgvs_forward", "mgvs_forward_losses",
+    "mgvs_abi_version", "mgvs_last_error", "mgvs_num_sums", "mgvs_workspace_bytes", "mgvs_workspace_bytes_ex", "mgvs_forward", "mgvs_forward_losses",
     "mgvs_finalize", "mgvs_backward", "mgvs_view_synthesis", "mgvs_reconstruct", "mgvs_project", "mgvs_test_div",
 )
 

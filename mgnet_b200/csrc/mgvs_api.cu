@@ -54,11 +54,11 @@ static bool make_map(TmaDesc* out, const float* base, int planes, int H, int W, 
     return r == CUDA_SUCCESS;
 }
 // TMA needs 16-byte aligned bases and row strides (W % 4 == 0); otherwise the kernels use their manual loaders.
-static bool tma_eligible(const MgvsProblem* p)
+static bool tma_eligible(const MgvsProblem* p, const float* tgt, const float* src0, const float* src1)
 {
     if (p->W % 4 != 0) return false;
     auto al = [](const void* q) { return ((uintptr_t)q & 15) == 0; };
-    if (!al(p->target) || !al(p->source[0]) || !al(p->source[1])) return false;
+    if (!al(tgt) || !al(src0) || !al(src1)) return false;
     for (int i = 0; i < p->n; i++)
         if (!al(p->inv_depth[i])) return false;
     return encode_fn() != nullptr;
@@ -67,11 +67,11 @@ static bool tma_eligible(const MgvsProblem* p)
 // ---------------------------------------------------------------------------------------------
 // workspace layout (all offsets 256-byte aligned)
 struct Layout {
-    size_t cams, partials, imgsums, counter, pose_partials, packed[S], total;
+    size_t cams, partials, imgsums, counter, pose_partials, packed[S], planar[1 + S], total;
     int tiles_x, tiles_y, tiles;
 };
 static inline size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
-static Layout make_layout(int B, int H, int W, int n)
+static Layout make_layout(int B, int H, int W, int n, int image_dtype = 0)
 {
     Layout L;
     L.tiles_x = (W + TW - 1) / TW;
@@ -85,6 +85,10 @@ static Layout make_layout(int B, int H, int W, int n)
     L.pose_partials = off; off = align256(off + sizeof(float) * (size_t)L.tiles * 24);
     for (int s = 0; s < S; s++) {   // RGBA + 2-texel zero border copies of the sources
         L.packed[s] = off; off = align256(off + sizeof(float4) * (size_t)B * (H + 2 * PACK_BORDER) * (W + 2 * PACK_BORDER));
+    }
+    for (int k = 0; k < 1 + S; k++) {   // uint8 ingestion: float copies of target, prev, next ([B,3,H,W], 16-byte aligned for TMA)
+        L.planar[k] = off;
+        if (image_dtype == MGVS_IMAGE_U8) off = align256(off + sizeof(float) * (size_t)B * 3 * H * W);
     }
     L.total = off;
     return L;
@@ -168,6 +172,91 @@ __global__ void __launch_bounds__(256) pack_sources_kernel(int B, int H, int W, 
         }
         o0[idx] = a;
         o1[idx] = c;
+    }
+}
+
+// uint8 ingestion: the data loader hands over uint8 images and the reference's caller converts them
+// with `x.float() / 255.0` (mg_net.py:320-335).  This kernel applies exactly that -- one correctly rounded
+// fp32 division per value -- while it writes (a) the float planar copies the tile loads read and (b) the
+// packed RGBA copies of the two sources the gathers read, so the float images never cross PCIe (9 instead
+// of 36 bytes per pixel) and the sources are still read only once.  4 pixels per thread when W % 4 == 0.
+__device__ __forceinline__ float u8_to_unit(unsigned v) { return __fdiv_rn((float)v, 255.0f); }
+
+__global__ void __launch_bounds__(256) pack_u8_kernel(int B, int H, int W, const unsigned char* __restrict__ tg,
+                                                      const unsigned char* __restrict__ s0, const unsigned char* __restrict__ s1,
+                                                      float* __restrict__ ftg, float* __restrict__ f0, float* __restrict__ f1,
+                                                      float4* __restrict__ o0, float4* __restrict__ o1,
+                                                      const float* __restrict__ camera, long long cbs, long long crs,
+                                                      const float* __restrict__ poses, Cam* __restrict__ cams)
+{
+    if (blockIdx.x == gridDim.x - 1) {
+        for (int b = threadIdx.x; b < B; b += blockDim.x) prep_one(b, camera, cbs, crs, poses, cams);
+        return;
+    }
+    const int Wp = W + 2 * PACK_BORDER, Hp = H + 2 * PACK_BORDER;
+    const int HW = H * W;
+    const long long stride = (long long)(gridDim.x - 1) * blockDim.x;
+    const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    // zero border of the packed copies: 2 rows above / below, 2 columns left / right
+    const int nb_row = 2 * PACK_BORDER * Wp, nb_col = 2 * PACK_BORDER * H;
+    for (long long idx = tid; idx < (long long)B * (nb_row + nb_col); idx += stride) {
+        int b = (int)(idx / (nb_row + nb_col)), r = (int)(idx - (long long)b * (nb_row + nb_col));
+        int py, px;
+        if (r < nb_row) { int k = r / Wp; px = r - k * Wp; py = k < PACK_BORDER ? k : Hp - 2 * PACK_BORDER + k; }
+        else { r -= nb_row; int y = r / (2 * PACK_BORDER), k = r - y * (2 * PACK_BORDER); py = y + PACK_BORDER; px = k < PACK_BORDER ? k : Wp - 2 * PACK_BORDER + k; }
+        size_t o = ((size_t)b * Hp + py) * Wp + px;
+        o0[o] = z4; o1[o] = z4;
+    }
+    if ((W & 3) == 0) {
+        const int W4 = W >> 2;
+        const long long total = (long long)B * H * W4;
+        for (long long idx = tid; idx < total; idx += stride) {
+            int x4 = (int)(idx % W4);
+            long long t = idx / W4;
+            int y = (int)(t % H), b = (int)(t / H);
+            size_t base = (size_t)b * 3 * HW + (size_t)y * W + 4 * x4;
+            float v[3][3][4];      // [image][channel][pixel]
+            const unsigned char* im[3] = {tg, s0, s1};
+#pragma unroll
+            for (int k = 0; k < 3; k++)
+#pragma unroll
+                for (int c = 0; c < 3; c++) {
+                    unsigned w = *reinterpret_cast<const unsigned*>(im[k] + base + (size_t)c * HW);
+#pragma unroll
+                    for (int j = 0; j < 4; j++) v[k][c][j] = u8_to_unit((w >> (8 * j)) & 0xffu);
+                }
+            float* fo[3] = {ftg, f0, f1};
+#pragma unroll
+            for (int k = 0; k < 3; k++)
+#pragma unroll
+                for (int c = 0; c < 3; c++)
+                    *reinterpret_cast<float4*>(fo[k] + base + (size_t)c * HW) = make_float4(v[k][c][0], v[k][c][1], v[k][c][2], v[k][c][3]);
+            size_t o = ((size_t)b * Hp + (y + PACK_BORDER)) * Wp + (4 * x4 + PACK_BORDER);
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                o0[o + j] = make_float4(v[1][0][j], v[1][1][j], v[1][2][j], 0.f);
+                o1[o + j] = make_float4(v[2][0][j], v[2][1][j], v[2][2][j], 0.f);
+            }
+        }
+    } else {
+        const long long total = (long long)B * HW;
+        for (long long idx = tid; idx < total; idx += stride) {
+            int x = (int)(idx % W);
+            long long t = idx / W;
+            int y = (int)(t % H), b = (int)(t / H);
+            size_t base = (size_t)b * 3 * HW + (size_t)y * W + x;
+            float a[3], c[3];
+#pragma unroll
+            for (int ch = 0; ch < 3; ch++) {
+                ftg[base + (size_t)ch * HW] = u8_to_unit(tg[base + (size_t)ch * HW]);
+                a[ch] = u8_to_unit(s0[base + (size_t)ch * HW]); f0[base + (size_t)ch * HW] = a[ch];
+                c[ch] = u8_to_unit(s1[base + (size_t)ch * HW]); f1[base + (size_t)ch * HW] = c[ch];
+            }
+            size_t o = ((size_t)b * Hp + (y + PACK_BORDER)) * Wp + (x + PACK_BORDER);
+            o0[o] = make_float4(a[0], a[1], a[2], 0.f);
+            o1[o] = make_float4(c[0], c[1], c[2], 0.f);
+        }
     }
 }
 
@@ -405,7 +494,8 @@ static int check_problem(const MgvsProblem* p)
     if (p->reduce_op != 0) return fail(MGVS_EUNSUPPORTED, "photometric_reduce_op: only 'min' is implemented");
     if (!(p->ssim_weight > 0.f)) return fail(MGVS_EUNSUPPORTED, "ssim_loss_weight must be > 0 (the L1-only branch of loss.py:195-196 is not implemented)");
     if (!p->workspace || ((uintptr_t)p->workspace & 255)) return fail(MGVS_EINVAL, "workspace null or not 256-byte aligned");
-    if (p->workspace_bytes < make_layout(p->B, p->H, p->W, p->n).total) return fail(MGVS_EWORKSPACE, "workspace too small");
+    if (p->image_dtype != MGVS_IMAGE_F32 && p->image_dtype != MGVS_IMAGE_U8) return fail(MGVS_EINVAL, "image_dtype must be MGVS_IMAGE_F32 or MGVS_IMAGE_U8");
+    if (p->workspace_bytes < make_layout(p->B, p->H, p->W, p->n, p->image_dtype).total) return fail(MGVS_EWORKSPACE, "workspace too small");
     return MGVS_OK;
 }
 
@@ -429,11 +519,13 @@ int mgvs_abi_version(void) { return MGVS_ABI_VERSION; }
 const char* mgvs_last_error(void) { return g_err; }
 int mgvs_num_sums(int n) { return 3 * n + 3; }
 
-size_t mgvs_workspace_bytes(int B, int H, int W, int n)
+size_t mgvs_workspace_bytes_ex(int B, int H, int W, int n, int image_dtype)
 {
     if (B < 1 || H < 1 || W < 1 || n < 1 || n > MGVS_MAX_SCALES) return 0;
-    return make_layout(B, H, W, n).total;
+    if (image_dtype != MGVS_IMAGE_F32 && image_dtype != MGVS_IMAGE_U8) return 0;
+    return make_layout(B, H, W, n, image_dtype).total;
 }
+size_t mgvs_workspace_bytes(int B, int H, int W, int n) { return mgvs_workspace_bytes_ex(B, H, W, n, MGVS_IMAGE_F32); }
 
 int mgvs_forward_losses(const MgvsProblem* p, unsigned char* sel, double* sums, float* losses, void* cuda_stream)
 {
@@ -441,32 +533,43 @@ int mgvs_forward_losses(const MgvsProblem* p, unsigned char* sel, double* sums, 
     if (rc) return rc;
     if (!sums) return fail(MGVS_EINVAL, "null sums");
     cudaStream_t st = (cudaStream_t)cuda_stream;
-    Layout L = make_layout(p->B, p->H, p->W, p->n);
+    Layout L = make_layout(p->B, p->H, p->W, p->n, p->image_dtype);
     char* ws = (char*)p->workspace;
     Cam* cams = (Cam*)(ws + L.cams);
+    // float views of the three images: the caller's tensors, or the workspace copies written by pack_u8_kernel
+    const bool u8 = p->image_dtype == MGVS_IMAGE_U8;
+    const float* tgt_f = u8 ? (const float*)(ws + L.planar[0]) : (const float*)p->target;
+    const float* src_f[S] = {u8 ? (const float*)(ws + L.planar[1]) : (const float*)p->source[0],
+                             u8 ? (const float*)(ws + L.planar[2]) : (const float*)p->source[1]};
     cudaMemsetAsync(ws + L.counter, 0, 256, st);   // arrival counter of reduce_kernel (workspace arrives uninitialised)
     FwdParams fp;
     memset(&fp, 0, sizeof(fp));
     fp.B = p->B; fp.H = p->H; fp.W = p->W; fp.n = p->n; fp.automask = p->automask;
-    fp.tgt = p->target; fp.src[0] = p->source[0]; fp.src[1] = p->source[1];
+    fp.tgt = tgt_f; fp.src[0] = src_f[0]; fp.src[1] = src_f[1];
     for (int i = 0; i < p->n; i++) fp.inv[i] = p->inv_depth[i];
     fp.mask = p->mask; fp.cams = cams; fp.sel = sel;
     fp.psrc[0] = (const float4*)(ws + L.packed[0]); fp.psrc[1] = (const float4*)(ws + L.packed[1]);
     {
         long long texels = (long long)p->B * (p->H + 2 * PACK_BORDER) * (p->W + 2 * PACK_BORDER);
         int blocks = (int)((texels + 255) / 256 < 148 * 16 ? (texels + 255) / 256 : 148 * 16);
-        pack_sources_kernel<<<blocks + 1, 256, 0, st>>>(p->B, p->H, p->W, p->source[0], p->source[1], (float4*)(ws + L.packed[0]),
-                                                        (float4*)(ws + L.packed[1]), p->camera, p->cam_batch_stride, p->cam_row_stride, p->poses, cams);
+        if (u8)
+            pack_u8_kernel<<<blocks + 1, 256, 0, st>>>(p->B, p->H, p->W, (const unsigned char*)p->target, (const unsigned char*)p->source[0],
+                                                       (const unsigned char*)p->source[1], (float*)(ws + L.planar[0]), (float*)(ws + L.planar[1]),
+                                                       (float*)(ws + L.planar[2]), (float4*)(ws + L.packed[0]), (float4*)(ws + L.packed[1]),
+                                                       p->camera, p->cam_batch_stride, p->cam_row_stride, p->poses, cams);
+        else
+            pack_sources_kernel<<<blocks + 1, 256, 0, st>>>(p->B, p->H, p->W, src_f[0], src_f[1], (float4*)(ws + L.packed[0]),
+                                                            (float4*)(ws + L.packed[1]), p->camera, p->cam_batch_stride, p->cam_row_stride, p->poses, cams);
     }
     fp.partials = (double*)(ws + L.partials);
     fp.alpha = p->ssim_weight; fp.oma = p->one_minus_ssim_weight;
     fp.tiles_x = L.tiles_x; fp.tiles_y = L.tiles_y;
     FwdMaps maps;
-    bool use_tma = tma_eligible(p);
+    bool use_tma = tma_eligible(p, tgt_f, src_f[0], src_f[1]);
     if (use_tma) {
-        use_tma = make_map(&maps.tgt, p->target, 3 * p->B, p->H, p->W, FWD_ROWS, 3) &&
-                  make_map(&maps.src[0], p->source[0], 3 * p->B, p->H, p->W, FWD_ROWS, 3) &&
-                  make_map(&maps.src[1], p->source[1], 3 * p->B, p->H, p->W, FWD_ROWS, 3);
+        use_tma = make_map(&maps.tgt, tgt_f, 3 * p->B, p->H, p->W, FWD_ROWS, 3) &&
+                  make_map(&maps.src[0], src_f[0], 3 * p->B, p->H, p->W, FWD_ROWS, 3) &&
+                  make_map(&maps.src[1], src_f[1], 3 * p->B, p->H, p->W, FWD_ROWS, 3);
         for (int i = 0; i < p->n && use_tma; i++) use_tma = make_map(&maps.inv[i], p->inv_depth[i], p->B, p->H, p->W, FWD_ROWS, 1);
     }
     if (use_tma) {
@@ -503,12 +606,16 @@ int mgvs_backward(const MgvsProblem* p, const unsigned char* sel, const double* 
     if (rc) return rc;
     if (!sel || !sums || !g_losses || !grad_inv || !grad_poses) return fail(MGVS_EINVAL, "null argument");
     cudaStream_t st = (cudaStream_t)cuda_stream;
-    Layout L = make_layout(p->B, p->H, p->W, p->n);
+    Layout L = make_layout(p->B, p->H, p->W, p->n, p->image_dtype);
     char* ws = (char*)p->workspace;
+    const bool u8 = p->image_dtype == MGVS_IMAGE_U8;     // float copies were written by the forward (pack_u8_kernel)
+    const float* tgt_f = u8 ? (const float*)(ws + L.planar[0]) : (const float*)p->target;
+    const float* src_f[S] = {u8 ? (const float*)(ws + L.planar[1]) : (const float*)p->source[0],
+                             u8 ? (const float*)(ws + L.planar[2]) : (const float*)p->source[1]};
     BwdParams bp;
     memset(&bp, 0, sizeof(bp));
     bp.B = p->B; bp.H = p->H; bp.W = p->W; bp.n = p->n; bp.automask = p->automask;
-    bp.tgt = p->target; bp.src[0] = p->source[0]; bp.src[1] = p->source[1];
+    bp.tgt = tgt_f; bp.src[0] = src_f[0]; bp.src[1] = src_f[1];
     for (int i = 0; i < p->n; i++) {
         bp.inv[i] = p->inv_depth[i];
         if (!grad_inv[i]) return fail(MGVS_EINVAL, "null grad_inv pointer");
@@ -522,9 +629,9 @@ int mgvs_backward(const MgvsProblem* p, const unsigned char* sel, const double* 
     bp.photo_w = p->photometric_weight; bp.smooth_w = p->smoothing_weight;
     bp.tiles_x = L.tiles_x; bp.tiles_y = L.tiles_y;
     BwdMaps maps;
-    bool use_tma = tma_eligible(p);
+    bool use_tma = tma_eligible(p, tgt_f, src_f[0], src_f[1]);
     if (use_tma) {
-        use_tma = make_map(&maps.tgt, p->target, 3 * p->B, p->H, p->W, BWD_ROWS, 3);
+        use_tma = make_map(&maps.tgt, tgt_f, 3 * p->B, p->H, p->W, BWD_ROWS, 3);
         for (int i = 0; i < p->n && use_tma; i++) use_tma = make_map(&maps.inv[i], p->inv_depth[i], p->B, p->H, p->W, BWD_ROWS, 1);
     }
     if (use_tma) {

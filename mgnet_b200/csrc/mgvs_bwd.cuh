@@ -288,8 +288,10 @@ __global__ void __launch_bounds__(NT, MIN_CTAS) bwd_kernel(const BwdParams p, co
             }
         }
         // ---- stage A: warp both sources on tile+2 (software pipelined, mgvs_device.cuh) ----
+#ifndef MGVS_SKIP_A
         warp_tile<2, BWD_ROWS, BWD_CH, USE_TMA>(sX, sX + 3 * BWD_CH, sI, inv, src0, src1, sCam, x0, y0, H, W, border,
                                                  wm1, hm1, rw, rh, tid);
+#endif
         __syncthreads();
 
         float G[S][3][4];
@@ -303,7 +305,12 @@ __global__ void __launch_bounds__(NT, MIN_CTAS) bwd_kernel(const BwdParams p, co
                     int pr = h / BWD_PW, pc = h - pr * BWD_PW;
                     float ca = 0.f, cb = 0.f, cc = 0.f;
                     unsigned s = psel[it];
+#ifdef MGVS_SKIP_B
+                    if (s < 2) { ca = sX[pr * PITCH + pc]; cb = ca; cc = ca; }
+                    if (false) {
+#else
                     if (s < 2) {
+#endif
                         // window rows pr..pr+2, cols pc..pc+2 in tile+2 coordinates
                         const float* xw = sX + s * 3 * BWD_CH + ch * BWD_CH + pr * PITCH + XOFF - 2 + pc;
                         const float* yw = sY + ch * BWD_CH + pr * PITCH + XOFF - 2 + pc;
@@ -344,8 +351,12 @@ __global__ void __launch_bounds__(NT, MIN_CTAS) bwd_kernel(const BwdParams p, co
             {
                 float box[S][3][4];
                 const float4* mp = sCo + ty * PITCH + XOFF + 4 * tx;
+#ifdef MGVS_SKIP_C
+                for (int s = 0; s < S; s++) for (int m = 0; m < 3; m++) for (int k = 0; k < 4; k++) box[s][m][k] = mp[k].x;
+#else
                 if (border) box_adjoint4<true>(mp, rwgt, cwgt, box);
                 else box_adjoint4<false>(mp, rwgt, cwgt, box);
+#endif
 #pragma unroll
                 for (int s = 0; s < S; s++)
 #pragma unroll
@@ -412,6 +423,9 @@ __global__ void __launch_bounds__(NT, MIN_CTAS) bwd_kernel(const BwdParams p, co
                     g2 += cf_l1 * (d2 > 0.f ? 1.f : (d2 < 0.f ? -1.f : 0.f));
                 }
                 if (g0 == 0.f && g1 == 0.f && g2 == 0.f) continue;
+#ifdef MGVS_SKIP_D
+                ginv[k] += g0 + g1 + g2; continue;
+#endif
                 int u = u0 + k;
                 float r[3], Xc[3];
                 exact::ray(Kinv, u, v, r);

@@ -267,14 +267,20 @@ __global__ void __launch_bounds__(NT, MIN_CTAS) fwd_kernel(const FwdParams p, co
             tma::mbar_wait(sBar + 1 + (i & 1), (i >> 1) & 1);
         }
         // ---- stage 1: warp both sources at every halo pixel (software pipelined, mgvs_device.cuh) ----
+#ifndef MGVS_SKIP_S1
         warp_tile<1, FWD_ROWS, FWD_CH, USE_TMA>(sX, sX + FWD_TILE3_FLOATS, sI, inv, src0, src1, sCam, x0, y0, H, W, border,
                                                  wm1, hm1, rw, rh, tid);
+#endif
         __syncthreads();
 
         // ---- stage 2: photometric maps, min/argmin, smoothness ----
         float lw0[4], lw1[4];
+#ifndef MGVS_SKIP_S2
         photometric4(sX + ty * PITCH + XOFF + 4 * tx, ys_t, yst_t, p.alpha, p.oma, lw0);
         photometric4(sX + FWD_TILE3_FLOATS + ty * PITCH + XOFF + 4 * tx, ys_t, yst_t, p.alpha, p.oma, lw1);
+#else
+        for (int k = 0; k < 4; k++) { lw0[k] = sX[ty * PITCH + XOFF + 4 * tx + k]; lw1[k] = sX[FWD_TILE3_FLOATS + ty * PITCH + XOFF + 4 * tx + k]; }
+#endif
         float photo = 0.f;
         unsigned selw = 0;
 #pragma unroll

@@ -73,13 +73,18 @@ class MultiViewPhotometricLoss(nn.Module):
         self.n = len(inv_depths)
         assert pose_results.shape[1] == 2, "Context and poses lists must be of same length"
         # custom_fwd(cast_inputs=torch.float32) equivalent (mg_net.py:827): the op computes in fp32
+        # images: float in [0,1] as in the reference, or the data loader's uint8 tensors -- then the kernels apply
+        # the caller's `x.float() / 255.0` (mg_net.py:320-335) themselves, bit-identically
+        def img(t):
+            return t if t.dtype == torch.uint8 else t.float()
+
         with torch.autocast(device_type="cuda", enabled=False):
             lp, ls, sel = view_synthesis_loss(
                 [d.float() for d in inv_depths],
                 pose_results.float(),
-                targets["image_orig"].float(),
-                targets["image_prev_orig"].float(),
-                targets["image_next_orig"].float(),
+                img(targets["image_orig"]),
+                img(targets["image_prev_orig"]),
+                img(targets["image_next_orig"]),
                 targets["camera_matrix"].float(),
                 targets["reprojection_mask"] if "reprojection_mask" in targets else None,
                 self._config(),

@@ -54,8 +54,23 @@ def _require_cuda_f32(t: torch.Tensor, name: str, shape=None) -> torch.Tensor:
     return t.contiguous()
 
 
+def _require_cuda_image(t: torch.Tensor, name: str, shape=None) -> torch.Tensor:
+    """Images may arrive as float (what the reference loss receives) or as the data loader's uint8
+    (mg_net.py:320-335 converts with ``.float() / 255.0``; the library does that conversion itself)."""
+    if isinstance(t, torch.Tensor) and t.dtype == torch.uint8:
+        if not t.is_cuda:
+            raise RuntimeError("%s is on %s: the view-synthesis loss runs only on CUDA (sm_100a); there is no CPU fallback" % (name, t.device))
+        if shape is not None and tuple(t.shape) != tuple(shape):
+            raise ValueError("%s has shape %s, expected %s" % (name, tuple(t.shape), tuple(shape)))
+        return t.contiguous()
+    return _require_cuda_f32(t, name, shape)
+
+
 def _fill_problem(prob, cfg, tgt, prev, nxt, inv, camera, poses, mask, ws):
     B, _, H, W = tgt.shape
+    if not (tgt.dtype == prev.dtype == nxt.dtype):
+        raise TypeError("image_orig, image_prev_orig and image_next_orig must share one dtype (float32 or uint8)")
+    prob.image_dtype = _lib.IMAGE_U8 if tgt.dtype == torch.uint8 else _lib.IMAGE_F32
     prob.B, prob.H, prob.W, prob.n = B, H, W, len(inv)
     prob.target = tgt.data_ptr()
     prob.source[0] = prev.data_ptr()
@@ -91,12 +106,15 @@ class _ViewSynthesisLoss(torch.autograd.Function):
         n = len(inv)
         if n < 1 or n > _lib.MAX_SCALES:
             raise ValueError("need 1..%d inverse-depth maps, got %d" % (_lib.MAX_SCALES, n))
-        tgt = _require_cuda_f32(tgt, "image_orig")
+        tgt = _require_cuda_image(tgt, "image_orig")
         B, C, H, W = tgt.shape
         if C != 3:
             raise ValueError("image_orig must be [B,3,H,W]")
-        prev = _require_cuda_f32(prev, "image_prev_orig", (B, 3, H, W))
-        nxt = _require_cuda_f32(nxt, "image_next_orig", (B, 3, H, W))
+        prev = _require_cuda_image(prev, "image_prev_orig", (B, 3, H, W))
+        nxt = _require_cuda_image(nxt, "image_next_orig", (B, 3, H, W))
+        if not (tgt.dtype == prev.dtype == nxt.dtype):
+            raise TypeError("image_orig, image_prev_orig and image_next_orig must share one dtype (float32 or uint8)")
+        img_dtype = _lib.IMAGE_U8 if tgt.dtype == torch.uint8 else _lib.IMAGE_F32
         inv = [_require_cuda_f32(d, "depth[%d]" % i, (B, 1, H, W)) for i, d in enumerate(inv)]
         poses = _require_cuda_f32(poses, "poses", (B, 2, 6))
         if camera.dim() != 3 or camera.shape[0] != B or camera.shape[1] < 3 or camera.shape[2] < 3:
@@ -112,7 +130,7 @@ class _ViewSynthesisLoss(torch.autograd.Function):
             mask = mask.contiguous()
         dev = tgt.device
         with torch.cuda.device(dev):
-            ws = torch.empty(int(L.mgvs_workspace_bytes(B, H, W, n)), dtype=torch.uint8, device=dev)
+            ws = torch.empty(int(L.mgvs_workspace_bytes_ex(B, H, W, n, img_dtype)), dtype=torch.uint8, device=dev)
             sel = torch.empty((n, B, H, W), dtype=torch.uint8, device=dev)
             sums = torch.empty(3 * n + 3, dtype=torch.float64, device=dev)
             losses = torch.empty(2, dtype=torch.float32, device=dev)

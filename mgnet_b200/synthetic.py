@@ -10,7 +10,7 @@ from __future__ import annotations
 import torch
 import torch.nn.functional as F
 
-__all__ = ["make_inputs", "kitti_like_K", "bytes_per_pixel", "snap_pose_trig"]
+__all__ = ["make_inputs", "kitti_like_K", "bytes_per_pixel", "snap_pose_trig", "quantize_images"]
 
 
 def _gen(seed: int) -> torch.Generator:
@@ -123,6 +123,20 @@ def make_inputs(
         targets["reprojection_mask"] = torch.rand(B, 1, H, W, generator=g) < mask_keep
     predictions = {"depth": inv_depths, "poses": poses}
     return predictions, targets
+
+
+IMAGE_KEYS = ("image_orig", "image_prev_orig", "image_next_orig")
+
+
+def quantize_images(targets):
+    """Returns (targets_u8, targets_f32): the three images as the data loader's uint8 tensors and as what the
+    reference's caller makes of them, ``x.float() / 255.0`` (mg_net.py:320-335).  Other entries are shared."""
+    tu, tf = dict(targets), dict(targets)
+    for k in IMAGE_KEYS:
+        u = (targets[k] * 255.0).round().clamp_(0, 255).to(torch.uint8).contiguous()
+        tu[k] = u
+        tf[k] = (u.float() / 255.0).contiguous()
+    return tu, tf
 
 
 def bytes_per_pixel(n: int, S: int = 2, mask: bool = True, fwd_only: bool = False) -> int:
