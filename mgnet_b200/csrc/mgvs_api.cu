@@ -152,6 +152,7 @@ __global__ void __launch_bounds__(256) pack_sources_kernel(int B, int H, int W, 
                                                            const float* __restrict__ camera, long long cbs, long long crs,
                                                            const float* __restrict__ poses, Cam* __restrict__ cams)
 {
+    pdl_trigger();     // fwd_kernel may start its prologue (it waits before reading what this kernel writes)
     if (blockIdx.x == gridDim.x - 1) {
         for (int b = threadIdx.x; b < B; b += blockDim.x) prep_one(b, camera, cbs, crs, poses, cams);
         return;
@@ -189,6 +190,7 @@ __global__ void __launch_bounds__(256) pack_u8_kernel(int B, int H, int W, const
                                                       const float* __restrict__ camera, long long cbs, long long crs,
                                                       const float* __restrict__ poses, Cam* __restrict__ cams)
 {
+    pdl_trigger();
     if (blockIdx.x == gridDim.x - 1) {
         for (int b = threadIdx.x; b < B; b += blockDim.x) prep_one(b, camera, cbs, crs, poses, cams);
         return;
@@ -284,6 +286,7 @@ __global__ void __launch_bounds__(256) reduce_kernel(int B, int n, int tiles_per
     __shared__ bool last;
     __shared__ double sh_sums[3 * MAXN + 3];
     const int b = blockIdx.x, nq = 4 * n + 3, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    pdl_wait();        // launched early (programmatic dependent launch): the partials come from fwd_kernel
     // one warp per quantity: lanes stride over the tiles of image b, then a fixed-order xor butterfly
     for (int q = warp; q < nq; q += 8) {
         double acc = 0.0;
@@ -499,6 +502,21 @@ static int check_problem(const MgvsProblem* p)
     return MGVS_OK;
 }
 
+// Launch with the programmatic-stream-serialization attribute: the kernel may begin while its predecessor in the
+// stream is still running and synchronises on it with pdl_wait() (mgvs_device.cuh).
+template <typename... KArgs, typename... Args>
+static void launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args)
+{
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
+}
+
 static int check_launch(const char* what)
 {
     cudaError_t e = cudaGetLastError();
@@ -572,17 +590,18 @@ int mgvs_forward_losses(const MgvsProblem* p, unsigned char* sel, double* sums, 
                   make_map(&maps.src[1], src_f[1], 3 * p->B, p->H, p->W, FWD_ROWS, 3);
         for (int i = 0; i < p->n && use_tma; i++) use_tma = make_map(&maps.inv[i], p->inv_depth[i], p->B, p->H, p->W, FWD_ROWS, 1);
     }
+    fp.early_wait = u8 ? 1 : 0;
+    if (!use_tma) memset(&maps, 0, sizeof(maps));
     if (use_tma) {
         cudaFuncSetAttribute(fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FWD_SMEM_BYTES);
-        fwd_kernel<true><<<L.tiles, NT, FWD_SMEM_BYTES, st>>>(fp, maps);
+        launch_pdl(fwd_kernel<true>, dim3(L.tiles), dim3(NT), FWD_SMEM_BYTES, st, fp, maps);
     } else {
-        memset(&maps, 0, sizeof(maps));
         cudaFuncSetAttribute(fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, FWD_SMEM_BYTES);
-        fwd_kernel<false><<<L.tiles, NT, FWD_SMEM_BYTES, st>>>(fp, maps);
+        launch_pdl(fwd_kernel<false>, dim3(L.tiles), dim3(NT), FWD_SMEM_BYTES, st, fp, maps);
     }
-    reduce_kernel<<<p->B, 256, 0, st>>>(p->B, p->n, L.tiles_x * L.tiles_y, (long long)p->H * p->W, fp.partials,
-                                        (double*)(ws + L.imgsums), (unsigned int*)(ws + L.counter), sums,
-                                        p->photometric_weight, p->smoothing_weight, losses);
+    launch_pdl(reduce_kernel, dim3(p->B), dim3(256), 0, st, p->B, p->n, L.tiles_x * L.tiles_y, (long long)p->H * p->W,
+               (const double*)fp.partials, (double*)(ws + L.imgsums), (unsigned int*)(ws + L.counter), sums,
+               p->photometric_weight, p->smoothing_weight, losses);
     return check_launch("mgvs_forward");
 }
 

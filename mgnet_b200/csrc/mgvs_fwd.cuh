@@ -16,6 +16,7 @@ namespace mgvs {
 
 struct FwdParams {
     int B, H, W, n, automask;
+    int early_wait;              // the image pointers are workspace copies written by the preceding kernel (uint8 ingestion)
     const float* tgt;
     const float* src[S];
     const float* inv[MAXN];
@@ -127,6 +128,7 @@ __global__ void __launch_bounds__(NT, MIN_CTAS) fwd_kernel(const FwdParams p, co
     const int u0 = x0 + 4 * tx, v = y0 + ty;     // this thread's 4 outputs: (v, u0..u0+3)
 
     const bool border = (x0 == 0) || (y0 == 0) || (x0 + TW >= W) || (y0 + TH >= H);
+    if (p.early_wait) pdl_wait();
     if (USE_TMA) {
         if (tid == 0) {
             tma::mbar_init(sBar + 0, 1); tma::mbar_init(sBar + 1, 1); tma::mbar_init(sBar + 2, 1);
@@ -138,8 +140,7 @@ __global__ void __launch_bounds__(NT, MIN_CTAS) fwd_kernel(const FwdParams p, co
             tma::mbar_expect_tx(sBar + 1, FWD_CH * 4);
             tma::load_3d(sInv, &maps.inv[0], x0 - XOFF, y0 - 1, b, sBar + 1);
         }
-        if (tid < 48) sCam[tid] = reinterpret_cast<const float*>(p.cams + b)[tid];
-        __syncthreads();                 // barrier init + camera table visible
+        __syncthreads();                 // barrier init visible
         tma::mbar_wait(sBar + 0, 0);
         if (border) {                    // CTA-uniform
             // the three tiles are contiguous planes of FWD_TILE3_FLOATS / FWD_CH floats: patch them in one go
@@ -149,7 +150,6 @@ __global__ void __launch_bounds__(NT, MIN_CTAS) fwd_kernel(const FwdParams p, co
             __syncthreads();
         }
     } else {
-        if (tid < 48) sCam[tid] = reinterpret_cast<const float*>(p.cams + b)[tid];
         fwd_load_tile(p.tgt + (size_t)b * 3 * HW, sY, x0, y0, H, W, tid);
         fwd_load_tile(p.src[0] + (size_t)b * 3 * HW, sX, x0, y0, H, W, tid);
         fwd_load_tile(p.src[1] + (size_t)b * 3 * HW, sX + FWD_TILE3_FLOATS, x0, y0, H, W, tid);
@@ -245,7 +245,12 @@ __global__ void __launch_bounds__(NT, MIN_CTAS) fwd_kernel(const FwdParams p, co
         cntX += hx ? 1.f : 0.f;
         cntY += hy ? 1.f : 0.f;
     }
-    __syncthreads();   // identity evaluation done: sX may be overwritten
+    // Everything above reads only the caller's tensors.  The camera table and the packed source copies are written
+    // by pack_sources_kernel, which may still be running (programmatic dependent launch): wait for it here.
+    pdl_wait();
+    pdl_trigger();     // let reduce_kernel's CTAs be scheduled; they wait for this grid to finish
+    if (tid < 48) sCam[tid] = reinterpret_cast<const float*>(p.cams + b)[tid];
+    __syncthreads();   // identity evaluation done: sX may be overwritten; camera table visible
 
     const int nq = 4 * p.n + 3;
     double* my_partials = p.partials + (size_t)tile * nq;
