@@ -153,6 +153,9 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--backward", default="stash", choices=["stash", "recompute"],
+                    help="stash: the forward writes the SSIM-adjoint coefficient texels and the backward consumes them (default, "
+                         "fastest); recompute: the backward recomputes the forward from the same tiles (lean memory)")
     ap.add_argument("--e2e-images", default="uint8", choices=["uint8", "float32"],
                     help="dtype of the host images of the e2e leg (uint8 = what the reference's data loader produces)")
     args = ap.parse_args()
@@ -195,7 +198,7 @@ def main():
     from mgnet_b200 import MultiViewPhotometricLoss, _lib, ops
     from mgnet_b200.synthetic import make_inputs
     L = _lib.lib()
-    mod = MultiViewPhotometricLoss(process_group=group, ddp_grad_scale=False, **HP)
+    mod = MultiViewPhotometricLoss(process_group=group, ddp_grad_scale=False, backward=args.backward, **HP)
 
     # rotating input sets so that no step finds its inputs in L2 (inputs of one set are < L2 for c1/c2)
     in_bytes = B * H * W * (36 + 4 * n + 1)
@@ -253,6 +256,7 @@ def main():
     from mgnet_b200.ops import LossConfig, _fill_problem
     cfg = LossConfig(**HP)
     ws = torch.empty(int(L.mgvs_workspace_bytes(B, H, W, n)), dtype=torch.uint8, device=dev)
+    stash = torch.empty(int(L.mgvs_stash_bytes(B, H, W, n)), dtype=torch.uint8, device=dev) if args.backward == "stash" else None
     sel = torch.empty((n, B, H, W), dtype=torch.uint8, device=dev)
     sums = torch.empty(3 * n + 3, dtype=torch.float64, device=dev)
     losses = torch.empty(2, dtype=torch.float32, device=dev)
@@ -267,7 +271,7 @@ def main():
         prob = _lib.MgvsProblem()
         inv_k = [d.detach() for d in pk["depth"]]
         _fill_problem(prob, cfg, tk["image_orig"], tk["image_prev_orig"], tk["image_next_orig"], inv_k,
-                      tk["camera_matrix"], pk["poses"].detach(), tk.get("reprojection_mask"), ws)
+                      tk["camera_matrix"], pk["poses"].detach(), tk.get("reprojection_mask"), ws, stash)
         a, b_, c = (torch.cuda.Event(enable_timing=True) for _ in range(3))
         a.record()
         _lib.check(L.mgvs_forward_losses(ctypes.byref(prob), sel.data_ptr(), sums.data_ptr(), losses.data_ptr(), stream))
@@ -287,7 +291,8 @@ def main():
     traffic = None
     try:
         with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
-            traffic = json.load(f).get(args.workload, {}).get(dominant + "_kernel_dram_bytes_per_launch")
+            traffic = json.load(f).get(args.workload, {}).get(
+                dominant + ("_stash" if args.backward == "stash" else "") + "_kernel_dram_bytes_per_launch")
     except Exception:
         pass
     roofline = {"bound": "hbm", "kernel": dominant + "_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
@@ -388,7 +393,8 @@ def main():
             "config": {"workload": desc, "B_per_gpu": B, "H": H, "W": W, "scales": n, "sources": 2, "mask": True,
                        "l2": "rotating %d input sets (%.0f MB) so inputs are never L2-resident" % (nsets, nsets * in_bytes / 1e6),
                        "parallelism": "batch-sharded x%d, one NCCL all-reduce of %d doubles per step" % (world, 3 * n + 3) if world > 1 else "single GPU",
-                       "bytes_per_pixel_fwd_bwd": bpp["fwd_bwd"]},
+                       "bytes_per_pixel_fwd_bwd": bpp["fwd_bwd"], "backward": args.backward,
+                       "stash_bytes_per_pixel": (96 * n if args.backward == "stash" else 0)},
             "roofline": roofline, "cpu_baseline": cpu_base, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
             "hbm_frac_fwd_bwd": value / world * bpp["fwd_bwd"] / peak,
         }

@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define MGVS_ABI_VERSION 2
+#define MGVS_ABI_VERSION 3
 #define MGVS_MAX_SCALES 8   /* n: number of inverse-depth maps (reference: 3, mg_net.py:760-764) */
 #define MGVS_NUM_SOURCES 2  /* S: prev, next -- hard-coded in the reference (loss.py:116) */
 
@@ -68,6 +68,14 @@ typedef struct MgvsProblem {
                                    the library applies the caller's own conversion `x.float() / 255.0`
                                    (mg_net.py:320-335) on the fly -- one correctly rounded division, so every
                                    result is bit-identical to the float path; host->device traffic drops 4x. */
+    void *stash;                /* optional, >= mgvs_stash_bytes(B,H,W,n) bytes, 256-byte aligned, or NULL.
+                                   Non-NULL selects the stash backward: mgvs_forward additionally writes the three
+                                   coefficients of the closed-form SSIM adjoint of the selected source per
+                                   (scale, channel, pixel) (48 B/px/scale) and mgvs_backward consumes them instead of
+                                   recomputing the warps and SSIM statistics (~2.5x fewer instructions; the path is
+                                   issue-bound, HBM is idle).  NULL keeps the recompute backward (nothing but `sel`
+                                   and the sums carried over).  Must stay untouched between forward and backward. */
+    size_t stash_bytes;
 } MgvsProblem;
 
 int mgvs_abi_version(void);
@@ -77,6 +85,9 @@ const char *mgvs_last_error(void);
 size_t mgvs_workspace_bytes(int B, int H, int W, int n);
 /* Same for a given image_dtype (uint8 ingestion keeps float copies of the three images in the workspace). */
 size_t mgvs_workspace_bytes_ex(int B, int H, int W, int n, int image_dtype);
+
+/* Size of the optional coefficient stash (MgvsProblem.stash). */
+size_t mgvs_stash_bytes(int B, int H, int W, int n);
 
 /* Number of doubles in the partial-sum vector: 3n+3 =
  *   [0,n)     sum over masked pixels of the per-pixel minimum photometric loss, per scale (loss.py:245)
@@ -103,8 +114,8 @@ int mgvs_forward_losses(const MgvsProblem *p, unsigned char *sel, double *sums, 
  *   losses [2] float out: loss_photometric, loss_smoothness. */
 int mgvs_finalize(const MgvsProblem *p, const double *sums, float *losses, void *cuda_stream);
 
-/* Fused backward (recomputes the forward from the same tiles).  Replaces the autograd replay of the
- * loss graph.
+/* Fused backward.  Replaces the autograd replay of the loss graph.  With p->stash == NULL it recomputes the
+ * forward from the same tiles; with the stash the forward filled it runs the box adjoint + per-output chain only.
  *   sel, sums   as produced by mgvs_forward (sums after the all-reduce if sharded)
  *   g_losses    [2] float, upstream gradients of (loss_photometric, loss_smoothness)
  *   grad_inv[i] [B,1,H,W] float out, fully overwritten

@@ -9,6 +9,7 @@
 
 #include "../../include/mgvs.h"
 #include "mgvs_bwd.cuh"
+#include "mgvs_bwd_stash.cuh"
 #include "mgvs_fwd.cuh"
 
 namespace mgvs {
@@ -53,6 +54,24 @@ static bool make_map(TmaDesc* out, const float* base, int planes, int H, int W, 
                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     return r == CUDA_SUCCESS;
 }
+// Coefficient stash (mgvs_bwd_stash.cuh): float4 texels [planes][H][4 phases][Wg groups] described as a 5-D map
+// {4 floats, Wg, 4, H, planes} with box {4, 18, 4, TH+2, 1}: one load fetches a whole channel map of a tile
+// (+1 halo row / column group on every side, zero-filled outside the image) in the layout stage C reads.
+static bool make_stash_map(TmaDesc* out, const void* base, int planes, int H, int Wg)
+{
+    EncodeTiledFn fn = encode_fn();
+    if (!fn) return false;
+    cuuint64_t dims[5] = {4, (cuuint64_t)Wg, 4, (cuuint64_t)H, (cuuint64_t)planes};
+    cuuint64_t strides[4] = {16, (cuuint64_t)Wg * 16, (cuuint64_t)Wg * 64, (cuuint64_t)Wg * 64 * (cuuint64_t)H};
+    cuuint32_t box[5] = {4, (cuuint32_t)BS_GROUPS, 4, (cuuint32_t)BS_ROWS, 1};
+    cuuint32_t es[5] = {1, 1, 1, 1, 1};
+    CUresult r = fn(reinterpret_cast<CUtensorMap*>(out), CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5, (void*)base, dims, strides, box, es,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS;
+}
+static size_t stash_bytes(int B, int H, int W, int n) { return (size_t)n * B * 3 * H * 4 * ((W + 3) / 4) * sizeof(float4); }
+
 // TMA needs 16-byte aligned bases and row strides (W % 4 == 0); otherwise the kernels use their manual loaders.
 static bool tma_eligible(const MgvsProblem* p, const float* tgt, const float* src0, const float* src1)
 {
@@ -499,6 +518,11 @@ static int check_problem(const MgvsProblem* p)
     if (!p->workspace || ((uintptr_t)p->workspace & 255)) return fail(MGVS_EINVAL, "workspace null or not 256-byte aligned");
     if (p->image_dtype != MGVS_IMAGE_F32 && p->image_dtype != MGVS_IMAGE_U8) return fail(MGVS_EINVAL, "image_dtype must be MGVS_IMAGE_F32 or MGVS_IMAGE_U8");
     if (p->workspace_bytes < make_layout(p->B, p->H, p->W, p->n, p->image_dtype).total) return fail(MGVS_EWORKSPACE, "workspace too small");
+    if (p->stash) {
+        if ((uintptr_t)p->stash & 255) return fail(MGVS_EINVAL, "stash not 256-byte aligned");
+        if (p->stash_bytes < stash_bytes(p->B, p->H, p->W, p->n)) return fail(MGVS_EWORKSPACE, "stash too small");
+        if (!encode_fn()) return fail(MGVS_ECUDA, "cuTensorMapEncodeTiled unavailable: the stash backward needs TMA");
+    }
     return MGVS_OK;
 }
 
@@ -544,6 +568,11 @@ size_t mgvs_workspace_bytes_ex(int B, int H, int W, int n, int image_dtype)
     return make_layout(B, H, W, n, image_dtype).total;
 }
 size_t mgvs_workspace_bytes(int B, int H, int W, int n) { return mgvs_workspace_bytes_ex(B, H, W, n, MGVS_IMAGE_F32); }
+size_t mgvs_stash_bytes(int B, int H, int W, int n)
+{
+    if (B < 1 || H < 1 || W < 1 || n < 1 || n > MGVS_MAX_SCALES) return 0;
+    return stash_bytes(B, H, W, n);
+}
 
 int mgvs_forward_losses(const MgvsProblem* p, unsigned char* sel, double* sums, float* losses, void* cuda_stream)
 {
@@ -592,12 +621,12 @@ int mgvs_forward_losses(const MgvsProblem* p, unsigned char* sel, double* sums, 
     }
     fp.early_wait = u8 ? 1 : 0;
     if (!use_tma) memset(&maps, 0, sizeof(maps));
-    if (use_tma) {
-        cudaFuncSetAttribute(fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FWD_SMEM_BYTES);
-        launch_pdl(fwd_kernel<true>, dim3(L.tiles), dim3(NT), FWD_SMEM_BYTES, st, fp, maps);
-    } else {
-        cudaFuncSetAttribute(fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, FWD_SMEM_BYTES);
-        launch_pdl(fwd_kernel<false>, dim3(L.tiles), dim3(NT), FWD_SMEM_BYTES, st, fp, maps);
+    fp.stash = (float4*)p->stash; fp.Wg = (p->W + 3) / 4;
+    {
+        void (*kern)(FwdParams, FwdMaps) = use_tma ? (p->stash ? fwd_kernel<true, true> : fwd_kernel<true, false>)
+                                                   : (p->stash ? fwd_kernel<false, true> : fwd_kernel<false, false>);
+        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, FWD_SMEM_BYTES);
+        launch_pdl(kern, dim3(L.tiles), dim3(NT), FWD_SMEM_BYTES, st, fp, maps);
     }
     launch_pdl(reduce_kernel, dim3(p->B), dim3(256), 0, st, p->B, p->n, L.tiles_x * L.tiles_y, (long long)p->H * p->W,
                (const double*)fp.partials, (double*)(ws + L.imgsums), (unsigned int*)(ws + L.counter), sums,
@@ -631,6 +660,38 @@ int mgvs_backward(const MgvsProblem* p, const unsigned char* sel, const double* 
     const float* tgt_f = u8 ? (const float*)(ws + L.planar[0]) : (const float*)p->target;
     const float* src_f[S] = {u8 ? (const float*)(ws + L.planar[1]) : (const float*)p->source[0],
                              u8 ? (const float*)(ws + L.planar[2]) : (const float*)p->source[1]};
+    if (p->stash) {
+        // stash backward: box adjoint of the forward's coefficient texels + per-output chain (mgvs_bwd_stash.cuh)
+        BwdSParams sp;
+        memset(&sp, 0, sizeof(sp));
+        sp.B = p->B; sp.H = p->H; sp.W = p->W; sp.n = p->n; sp.automask = p->automask;
+        sp.tgt = tgt_f;
+        for (int i = 0; i < p->n; i++) {
+            sp.inv[i] = p->inv_depth[i];
+            if (!grad_inv[i]) return fail(MGVS_EINVAL, "null grad_inv pointer");
+            sp.grad_inv[i] = grad_inv[i];
+        }
+        sp.mask = p->mask; sp.cams = (const Cam*)(ws + L.cams); sp.sel = sel; sp.sums = sums;
+        sp.psrc[0] = (const float4*)(ws + L.packed[0]); sp.psrc[1] = (const float4*)(ws + L.packed[1]);
+        sp.imgsums = (const double*)(ws + L.imgsums); sp.g_losses = g_losses;
+        sp.pose_partials = (float*)(ws + L.pose_partials);
+        sp.alpha = p->ssim_weight; sp.oma = p->one_minus_ssim_weight;
+        sp.photo_w = p->photometric_weight; sp.smooth_w = p->smoothing_weight;
+        sp.tiles_x = L.tiles_x; sp.tiles_y = L.tiles_y;
+        BwdSMaps smaps;
+        memset(&smaps, 0, sizeof(smaps));
+        if (!make_stash_map(&smaps.coef, p->stash, p->n * p->B * 3, p->H, (p->W + 3) / 4)) return fail(MGVS_ECUDA, "cuTensorMapEncodeTiled failed for the stash");
+        bool tma_img = tma_eligible(p, tgt_f, src_f[0], src_f[1]);
+        if (tma_img) {
+            tma_img = make_map(&smaps.tgt, tgt_f, 3 * p->B, p->H, p->W, BS_ROWS, 3);
+            for (int i = 0; i < p->n && tma_img; i++) tma_img = make_map(&smaps.inv[i], p->inv_depth[i], p->B, p->H, p->W, BS_ROWS, 1);
+        }
+        void (*kern)(BwdSParams, BwdSMaps) = tma_img ? bwd_stash_kernel<true> : bwd_stash_kernel<false>;
+        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, BS_SMEM_BYTES);
+        kern<<<L.tiles, NT, BS_SMEM_BYTES, st>>>(sp, smaps);
+        pose_reduce_kernel<<<p->B * S, 128, 0, st>>>(L.tiles_x * L.tiles_y, sp.pose_partials, p->poses, grad_poses);
+        return check_launch("mgvs_backward (stash)");
+    }
     BwdParams bp;
     memset(&bp, 0, sizeof(bp));
     bp.B = p->B; bp.H = p->H; bp.W = p->W; bp.n = p->n; bp.automask = p->automask;

@@ -24,6 +24,8 @@ struct FwdParams {
     const Cam* cams;
     const float4* psrc[S];       // packed RGBA + zero border copies of the sources (pack_sources_kernel)
     unsigned char* sel;          // may be null
+    float4* stash;               // STASH kernels only: SSIM-adjoint coefficient texels for the stash backward (see below)
+    int Wg;                      // ceil(W/4): column groups per stash row
     double* partials;            // [tiles][4n+3]
     float alpha, oma;
     int tiles_x, tiles_y;
@@ -60,8 +62,17 @@ __device__ __forceinline__ void fwd_load_tile(const float* __restrict__ img, flo
 // xs, ys: smem planes of the estimate and the target, pointing at [ch 0][halo row ty][my output 0]
 // (16B aligned); the 3x3 windows of the 4 outputs span columns -1..4 of rows 0..2 from there.
 // yst: target statistics at [0][ty][4*tx].
+//
+// KEEP: additionally hands the three coefficients of the closed-form SSIM adjoint of every
+// (channel, output) to emit(ch, k, a, b, c):  d(ssim)/d(x_q) for q in the 3x3 window of p is (a + b*x_q + c*y_q)/9
+// with a = ds/dmu_x, b = 2*ds/dE[xx], c = ds/dE[xy] -- zero where the clamp of loss.py:217 is inactive.  The
+// forward has every SSIM internal in registers here, so emitting them costs ~20 instructions per channel and
+// lets the stash backward skip the whole recomputation (tile+2 warps and SSIM statistics).
+struct NoEmit { __device__ __forceinline__ void operator()(int, int, float, float, float) const {} };
+
+template <bool KEEP, typename Emit>
 __device__ __forceinline__ void photometric4(const float* __restrict__ xs, const float* __restrict__ ys,
-                                             const float* __restrict__ yst, float alpha, float oma, float out[4])
+                                             const float* __restrict__ yst, float alpha, float oma, float out[4], Emit emit)
 {
     float ssum[4], lsum[4];
 #pragma unroll
@@ -94,7 +105,17 @@ __device__ __forceinline__ void photometric4(const float* __restrict__ xs, const
                     sgy4[4] = {sgy.x, sgy.y, sgy.z, sgy.w};
 #pragma unroll
         for (int k = 0; k < 4; k++) {
-            float l = exact::ssim_from_sums(sx[k], sxx[k], sxy[k], muy4[k], mys4[k], sgy4[k], nullptr);
+            exact::Ssim q;
+            float l = exact::ssim_from_sums(sx[k], sxx[k], sxy[k], muy4[k], mys4[k], sgy4[k], KEEP ? &q : nullptr);
+            if (KEEP) {
+                float id1 = exact::rcp_refined(q.d1), id2 = exact::rcp_refined(q.d2);
+                float idd = id1 * id2;
+                float ca = 2.f * muy4[k] * (q.n2 - q.n1) * idd - q.ssim * 2.f * q.mu_x * (id1 - id2);
+                float cb = -2.f * q.ssim * id2;
+                float cc = 2.f * q.n1 * idd;
+                bool ok = q.loss_raw >= 0.f && q.loss_raw <= 1.f;      // clamp passes gradient inclusively
+                emit(ch, k, ok ? ca : 0.f, ok ? cb : 0.f, ok ? cc : 0.f);
+            }
             if (ch == 0) { ssum[k] = l; lsum[k] = l1[k]; }
             else { ssum[k] = __fadd_rn(ssum[k], l); lsum[k] = __fadd_rn(lsum[k], l1[k]); }
         }
@@ -104,7 +125,7 @@ __device__ __forceinline__ void photometric4(const float* __restrict__ xs, const
         out[k] = __fadd_rn(__fmul_rn(alpha, exact::div3(ssum[k])), __fmul_rn(oma, exact::div3(lsum[k])));
 }
 
-template <bool USE_TMA>
+template <bool USE_TMA, bool STASH>
 __global__ void __launch_bounds__(NT, MIN_CTAS) fwd_kernel(const FwdParams p, const __grid_constant__ FwdMaps maps)
 {
     extern __shared__ __align__(128) float smem[];
@@ -219,8 +240,8 @@ __global__ void __launch_bounds__(NT, MIN_CTAS) fwd_kernel(const FwdParams p, co
     // identity-reprojection losses (un-warped source vs target), once per tile
     float lid0[4] = {0, 0, 0, 0}, lid1[4] = {0, 0, 0, 0};
     if (p.automask) {
-        photometric4(sX + ty * PITCH + XOFF + 4 * tx, ys_t, yst_t, p.alpha, p.oma, lid0);
-        photometric4(sX + FWD_TILE3_FLOATS + ty * PITCH + XOFF + 4 * tx, ys_t, yst_t, p.alpha, p.oma, lid1);
+        photometric4<false>(sX + ty * PITCH + XOFF + 4 * tx, ys_t, yst_t, p.alpha, p.oma, lid0, NoEmit());
+        photometric4<false>(sX + FWD_TILE3_FLOATS + ty * PITCH + XOFF + 4 * tx, ys_t, yst_t, p.alpha, p.oma, lid1, NoEmit());
     }
 
     // edge-aware smoothness weights exp(-mean_c |dI|) (depth.py:23-24), premultiplied by mask/validity
@@ -281,8 +302,27 @@ __global__ void __launch_bounds__(NT, MIN_CTAS) fwd_kernel(const FwdParams p, co
         // ---- stage 2: photometric maps, min/argmin, smoothness ----
         float lw0[4], lw1[4];
 #ifndef MGVS_SKIP_S2
-        photometric4(sX + ty * PITCH + XOFF + 4 * tx, ys_t, yst_t, p.alpha, p.oma, lw0);
-        photometric4(sX + FWD_TILE3_FLOATS + ty * PITCH + XOFF + 4 * tx, ys_t, yst_t, p.alpha, p.oma, lw1);
+        // STASH: coefficient texels (a, b, c, [source == 0]) of this scale, one float4 per (channel, pixel), in the
+        // phase-major layout [scale][image][channel][row][u & 3][u >> 2] -- for a fixed output k the 16 threads of a
+        // tile row write 256 contiguous bytes, and the backward's 3x3 taps are bank-conflict-free 128-bit loads.
+        // Source 0's texels are stored as they are produced; source 1's wait in registers for the argmin.
+        float4* st = nullptr;
+        const size_t st_ch = (size_t)H * 4 * p.Wg;
+        float c1[3][3][4];
+        // rows below the image and column groups right of it do not exist in the stash (the backward's TMA zero-fills them)
+        const bool row_ok = STASH && v < H && (x0 >> 2) + tx < p.Wg;
+        if (STASH) {
+            st = p.stash + ((size_t)i * p.B + b) * 3 * st_ch + (size_t)v * 4 * p.Wg + (x0 >> 2) + tx;
+            photometric4<true>(sX + ty * PITCH + XOFF + 4 * tx, ys_t, yst_t, p.alpha, p.oma, lw0,
+                               [&](int ch, int k, float a, float bq, float c) {
+                                   if (row_ok) st[ch * st_ch + k * p.Wg] = make_float4(a, bq, c, 1.f);
+                               });
+            photometric4<true>(sX + FWD_TILE3_FLOATS + ty * PITCH + XOFF + 4 * tx, ys_t, yst_t, p.alpha, p.oma, lw1,
+                               [&](int ch, int k, float a, float bq, float c) { c1[ch][0][k] = a; c1[ch][1][k] = bq; c1[ch][2][k] = c; });
+        } else {
+            photometric4<false>(sX + ty * PITCH + XOFF + 4 * tx, ys_t, yst_t, p.alpha, p.oma, lw0, NoEmit());
+            photometric4<false>(sX + FWD_TILE3_FLOATS + ty * PITCH + XOFF + 4 * tx, ys_t, yst_t, p.alpha, p.oma, lw1, NoEmit());
+        }
 #else
         for (int k = 0; k < 4; k++) { lw0[k] = sX[ty * PITCH + XOFF + 4 * tx + k]; lw1[k] = sX[FWD_TILE3_FLOATS + ty * PITCH + XOFF + 4 * tx + k]; }
 #endif
@@ -301,6 +341,17 @@ __global__ void __launch_bounds__(NT, MIN_CTAS) fwd_kernel(const FwdParams p, co
             }
             if (msk[k]) photo += best;
             selw |= bi << (8 * k);
+            if (STASH && row_ok) {
+                // fix up the eagerly stored texels: keep source 0's where it won, source 1's where it won, zeros elsewhere
+                // (identity reprojection selected, mask false, or outside the image)
+                const unsigned warp1 = p.automask ? 2u : 1u;
+                const bool w0 = msk[k] && bi == 0u, w1 = msk[k] && bi == warp1;
+                if (!w0) {
+#pragma unroll
+                    for (int ch = 0; ch < 3; ch++)
+                        st[ch * st_ch + k * p.Wg] = make_float4(w1 ? c1[ch][0][k] : 0.f, w1 ? c1[ch][1][k] : 0.f, w1 ? c1[ch][2][k] : 0.f, 0.f);
+                }
+            }
         }
         if (p.sel != nullptr && v < H) {
             unsigned char* sp = p.sel + ((size_t)i * p.B + b) * HW + (size_t)v * W + u0;

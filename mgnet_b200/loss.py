@@ -29,6 +29,7 @@ class MultiViewPhotometricLoss(nn.Module):
         padding_mode,
         process_group=None,
         ddp_grad_scale=False,
+        backward="stash",
     ):
         super().__init__()
         self.n = None
@@ -40,6 +41,7 @@ class MultiViewPhotometricLoss(nn.Module):
         self.padding_mode = padding_mode
         self.process_group = process_group
         self.ddp_grad_scale = ddp_grad_scale
+        self.backward = backward     # "stash" (fast, +48 B/px/scale of scratch) or "recompute" (lean memory), see ops.LossConfig
         self.last_selection = None   # uint8 [n,B,H,W] argmin of the most recent forward (new side output)
         # same assertion as the reference (loss.py:106-109)
         if self.automask_loss:
@@ -65,6 +67,7 @@ class MultiViewPhotometricLoss(nn.Module):
             padding_mode=self.padding_mode,
             process_group=self.process_group,
             ddp_grad_scale=bool(self.ddp_grad_scale),
+            backward=self.backward,
         )
 
     def forward(self, predictions, targets):

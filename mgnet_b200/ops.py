@@ -40,6 +40,11 @@ class LossConfig:
     process_group: object = None      # torch.distributed group for the partial-sum all-reduce (None = local)
     ddp_grad_scale: bool = False      # multiply local grads by world size so DDP's 1/G averaging yields the
                                       # full-batch gradient; only with process_group
+    backward: str = "stash"           # "stash": the forward also writes the SSIM-adjoint coefficient texels of the
+                                      # selected source (48 B/px/scale) and the backward consumes them (fastest);
+                                      # "recompute": nothing but the uint8 selection is carried over and the backward
+                                      # recomputes the forward from the same tiles (lean-memory mode).  Same results
+                                      # up to fp32 rounding of the gradients; forward outputs are bit-identical.
 
 
 def _require_cuda_f32(t: torch.Tensor, name: str, shape=None) -> torch.Tensor:
@@ -66,7 +71,7 @@ def _require_cuda_image(t: torch.Tensor, name: str, shape=None) -> torch.Tensor:
     return _require_cuda_f32(t, name, shape)
 
 
-def _fill_problem(prob, cfg, tgt, prev, nxt, inv, camera, poses, mask, ws):
+def _fill_problem(prob, cfg, tgt, prev, nxt, inv, camera, poses, mask, ws, stash=None):
     B, _, H, W = tgt.shape
     if not (tgt.dtype == prev.dtype == nxt.dtype):
         raise TypeError("image_orig, image_prev_orig and image_next_orig must share one dtype (float32 or uint8)")
@@ -91,6 +96,8 @@ def _fill_problem(prob, cfg, tgt, prev, nxt, inv, camera, poses, mask, ws):
     prob.padding_mode = 0
     prob.workspace = ws.data_ptr()
     prob.workspace_bytes = ws.numel()
+    prob.stash = stash.data_ptr() if stash is not None else None
+    prob.stash_bytes = stash.numel() if stash is not None else 0
 
 
 class _ViewSynthesisLoss(torch.autograd.Function):
@@ -129,13 +136,18 @@ class _ViewSynthesisLoss(torch.autograd.Function):
                 mask = mask != 0
             mask = mask.contiguous()
         dev = tgt.device
+        if cfg.backward not in ("stash", "recompute"):
+            raise ValueError("backward must be 'stash' or 'recompute', got %r" % (cfg.backward,))
+        # the stash is only worth writing when a backward pass will follow
+        want_stash = cfg.backward == "stash" and any(ctx.needs_input_grad[i] for i in (1,) + tuple(range(7, 7 + n)))
         with torch.cuda.device(dev):
             ws = torch.empty(int(L.mgvs_workspace_bytes_ex(B, H, W, n, img_dtype)), dtype=torch.uint8, device=dev)
+            stash = torch.empty(int(L.mgvs_stash_bytes(B, H, W, n)), dtype=torch.uint8, device=dev) if want_stash else None
             sel = torch.empty((n, B, H, W), dtype=torch.uint8, device=dev)
             sums = torch.empty(3 * n + 3, dtype=torch.float64, device=dev)
             losses = torch.empty(2, dtype=torch.float32, device=dev)
             prob = _lib.MgvsProblem()
-            _fill_problem(prob, cfg, tgt, prev, nxt, inv, camera, poses, mask, ws)
+            _fill_problem(prob, cfg, tgt, prev, nxt, inv, camera, poses, mask, ws, stash)
             stream = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
             world = 1
             if cfg.process_group is None:
@@ -152,6 +164,7 @@ class _ViewSynthesisLoss(torch.autograd.Function):
         ctx.cfg = cfg
         ctx.n = n
         ctx.has_mask = mask is not None
+        ctx.stash = stash            # raw scratch, not a differentiable tensor: kept on ctx like the workspace semantics
         ctx.grad_scale = float(world) if (cfg.ddp_grad_scale and cfg.process_group is not None) else 1.0
         saved = [poses, camera, tgt, prev, nxt, sel, sums, ws] + ([mask] if mask is not None else []) + list(inv)
         ctx.save_for_backward(*saved)
@@ -184,12 +197,13 @@ class _ViewSynthesisLoss(torch.autograd.Function):
             grads = [torch.empty_like(d) for d in inv]
             gp = torch.empty_like(poses)
             prob = _lib.MgvsProblem()
-            _fill_problem(prob, ctx.cfg, tgt, prev, nxt, inv, camera, poses, mask, ws)
+            _fill_problem(prob, ctx.cfg, tgt, prev, nxt, inv, camera, poses, mask, ws, ctx.stash)
             arr = (ctypes.c_void_p * len(grads))(*[x.data_ptr() for x in grads])
             stream = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
             _lib.check(L.mgvs_backward(ctypes.byref(prob), sel.data_ptr(), sums.data_ptr(), g.data_ptr(), arr,
                                        gp.data_ptr(), stream), "mgvs_backward")
             launch_counter.n += BWD_LAUNCHES
+        ctx.stash = None
         return (None, gp, None, None, None, None, None) + tuple(grads)
 
 

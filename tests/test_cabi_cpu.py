@@ -29,10 +29,12 @@ def test_header_symbols_exported():
 def test_host_side_queries():
     from mgnet_b200 import _lib
     L = _lib.lib()
-    assert L.mgvs_abi_version() == 2
+    assert L.mgvs_abi_version() == 3
     assert L.mgvs_num_sums(3) == 12
     ws = L.mgvs_workspace_bytes(16, 192, 640, 3)
     assert ws > 0 and ws % 256 == 0
+    assert L.mgvs_stash_bytes(16, 192, 640, 3) == 3 * 16 * 3 * 192 * 640 * 16   # 48 B per (pixel, scale)
+    assert L.mgvs_stash_bytes(1, 50, 70, 2) == 2 * 1 * 3 * 50 * 4 * 18 * 16         # ragged W: ceil(70/4) column groups
     assert L.mgvs_workspace_bytes(0, 192, 640, 3) == 0
     assert L.mgvs_workspace_bytes(1, 192, 640, 9) == 0
 
