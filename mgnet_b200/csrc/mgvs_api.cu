@@ -54,6 +54,8 @@ static bool make_map(TmaDesc* out, const float* base, int planes, int H, int W, 
                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     return r == CUDA_SUCCESS;
 }
+static inline size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
+
 // Coefficient stash (mgvs_bwd_stash.cuh): float4 texels [planes][H][4 phases][Wg groups] described as a 5-D map
 // {4 floats, Wg, 4, H, planes} with box {4, 18, 4, TH+2, 1}: one load fetches a whole channel map of a tile
 // (+1 halo row / column group on every side, zero-filled outside the image) in the layout stage C reads.
@@ -70,7 +72,9 @@ static bool make_stash_map(TmaDesc* out, const void* base, int planes, int H, in
                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     return r == CUDA_SUCCESS;
 }
-static size_t stash_bytes(int B, int H, int W, int n) { return (size_t)n * B * 3 * H * 4 * ((W + 3) / 4) * sizeof(float4); }
+// stash = coefficient texels [n][B][3][H][4][Wg] float4, then the two masked edge-aware weight planes [2B][H][4*Wg] floats
+static size_t stash_texel_bytes(int B, int H, int W, int n) { return align256((size_t)n * B * 3 * H * 4 * ((W + 3) / 4) * sizeof(float4)); }
+static size_t stash_bytes(int B, int H, int W, int n) { return stash_texel_bytes(B, H, W, n) + align256((size_t)2 * B * H * 4 * ((W + 3) / 4) * sizeof(float)); }
 
 // TMA needs 16-byte aligned bases and row strides (W % 4 == 0); otherwise the kernels use their manual loaders.
 static bool tma_eligible(const MgvsProblem* p, const float* tgt, const float* src0, const float* src1)
@@ -89,7 +93,6 @@ struct Layout {
     size_t cams, partials, imgsums, counter, pose_partials, packed[S], planar[1 + S], total;
     int tiles_x, tiles_y, tiles;
 };
-static inline size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
 static Layout make_layout(int B, int H, int W, int n, int image_dtype = 0)
 {
     Layout L;
@@ -622,6 +625,7 @@ int mgvs_forward_losses(const MgvsProblem* p, unsigned char* sel, double* sums, 
     fp.early_wait = u8 ? 1 : 0;
     if (!use_tma) memset(&maps, 0, sizeof(maps));
     fp.stash = (float4*)p->stash; fp.Wg = (p->W + 3) / 4;
+    fp.wgt = p->stash ? (float*)((char*)p->stash + stash_texel_bytes(p->B, p->H, p->W, p->n)) : nullptr;
     {
         void (*kern)(FwdParams, FwdMaps) = use_tma ? (p->stash ? fwd_kernel<true, true> : fwd_kernel<true, false>)
                                                    : (p->stash ? fwd_kernel<false, true> : fwd_kernel<false, false>);
@@ -680,7 +684,10 @@ int mgvs_backward(const MgvsProblem* p, const unsigned char* sel, const double* 
         sp.tiles_x = L.tiles_x; sp.tiles_y = L.tiles_y;
         BwdSMaps smaps;
         memset(&smaps, 0, sizeof(smaps));
-        if (!make_stash_map(&smaps.coef, p->stash, p->n * p->B * 3, p->H, (p->W + 3) / 4)) return fail(MGVS_ECUDA, "cuTensorMapEncodeTiled failed for the stash");
+        if (!make_stash_map(&smaps.coef, p->stash, p->n * p->B * 3, p->H, (p->W + 3) / 4) ||
+            !make_map(&smaps.wgt, (const float*)((const char*)p->stash + stash_texel_bytes(p->B, p->H, p->W, p->n)), 2 * p->B, p->H,
+                      4 * ((p->W + 3) / 4), BS_ROWS, 1))
+            return fail(MGVS_ECUDA, "cuTensorMapEncodeTiled failed for the stash");
         bool tma_img = tma_eligible(p, tgt_f, src_f[0], src_f[1]);
         if (tma_img) {
             tma_img = make_map(&smaps.tgt, tgt_f, 3 * p->B, p->H, p->W, BS_ROWS, 3);

@@ -26,6 +26,7 @@ struct FwdParams {
     unsigned char* sel;          // may be null
     float4* stash;               // STASH kernels only: SSIM-adjoint coefficient texels for the stash backward (see below)
     int Wg;                      // ceil(W/4): column groups per stash row
+    float* wgt;                  // STASH kernels only: masked edge-aware weight planes [2B][H][4*Wg] (pairs (q,q+1) and (q,q+W))
     double* partials;            // [tiles][4n+3]
     float alpha, oma;
     int tiles_x, tiles_y;
@@ -108,13 +109,15 @@ __device__ __forceinline__ void photometric4(const float* __restrict__ xs, const
             exact::Ssim q;
             float l = exact::ssim_from_sums(sx[k], sxx[k], sxy[k], muy4[k], mys4[k], sgy4[k], KEEP ? &q : nullptr);
             if (KEEP) {
-                float id1 = exact::rcp_refined(q.d1), id2 = exact::rcp_refined(q.d2);
-                float idd = id1 * id2;
-                float ca = 2.f * muy4[k] * (q.n2 - q.n1) * idd - q.ssim * 2.f * q.mu_x * (id1 - id2);
-                float cb = -2.f * q.ssim * id2;
-                float cc = 2.f * q.n1 * idd;
-                bool ok = q.loss_raw >= 0.f && q.loss_raw <= 1.f;      // clamp passes gradient inclusively
-                emit(ch, k, ok ? ca : 0.f, ok ? cb : 0.f, ok ? cc : 0.f);
+                // With e = 2/(d1 d2) (the reciprocal the SSIM division already refined; zero where the clamp of
+                // loss.py:217 is inactive):  a = e (mu_y (n2-n1) - ssim mu_x (d2-d1)),  b = -e ssim d1,  c = e n1
+                const bool ok = q.loss_raw >= 0.f && q.loss_raw <= 1.f;      // clamp passes gradient inclusively
+                const float e = ok ? q.idd + q.idd : 0.f;
+                const float sm = q.ssim * q.mu_x;
+                const float ca = e * fmaf(muy4[k], q.n2 - q.n1, -sm * (q.d2 - q.d1));
+                const float cb = -e * (q.ssim * q.d1);
+                const float cc = e * q.n1;
+                emit(ch, k, ca, cb, cc);
             }
             if (ch == 0) { ssum[k] = l; lsum[k] = l1[k]; }
             else { ssum[k] = __fadd_rn(ssum[k], l); lsum[k] = __fadd_rn(lsum[k], l1[k]); }
@@ -265,6 +268,12 @@ __global__ void __launch_bounds__(NT, MIN_CTAS) fwd_kernel(const FwdParams p, co
         cntN += msk[k] ? 1.f : 0.f;
         cntX += hx ? 1.f : 0.f;
         cntY += hy ? 1.f : 0.f;
+    }
+    if (STASH && v < H && (x0 >> 2) + tx < p.Wg) {
+        // the stash backward needs these weights at q, q-1 and q-W: leave them in the stash instead of having it redo the expf
+        float* wp = p.wgt + ((size_t)(2 * b) * H + v) * (4 * p.Wg) + u0;
+        *reinterpret_cast<float4*>(wp) = make_float4(wxm[0], wxm[1], wxm[2], wxm[3]);
+        *reinterpret_cast<float4*>(wp + (size_t)H * 4 * p.Wg) = make_float4(wym[0], wym[1], wym[2], wym[3]);
     }
     // Everything above reads only the caller's tensors.  The camera table and the packed source copies are written
     // by pack_sources_kernel, which may still be running (programmatic dependent launch): wait for it here.
