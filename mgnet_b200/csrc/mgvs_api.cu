@@ -524,6 +524,7 @@ static int check_problem(const MgvsProblem* p)
     if (p->stash) {
         if ((uintptr_t)p->stash & 255) return fail(MGVS_EINVAL, "stash not 256-byte aligned");
         if (p->stash_bytes < stash_bytes(p->B, p->H, p->W, p->n)) return fail(MGVS_EWORKSPACE, "stash too small");
+        if ((long long)3 * p->H * 4 * ((p->W + 3) / 4) >= (1ll << 31)) return fail(MGVS_EINVAL, "image too large for the stash's 32-bit texel offsets");
         if (!encode_fn()) return fail(MGVS_ECUDA, "cuTensorMapEncodeTiled unavailable: the stash backward needs TMA");
     }
     return MGVS_OK;

@@ -159,7 +159,11 @@ __global__ void __launch_bounds__(NT, MIN_CTAS) bwd_stash_kernel(const __grid_co
     const int H = p.H, W = p.W, HW = H * W;
     // vertical strips: lanes are consecutive columns (coalesced gathers and stores, conflict-free smem), each thread
     // owns rows v0..v0+3 of column u
-    const int tx = tid & (BS_SX - 1), sy = tid / BS_SX;
+    // Within a warp (32 columns) lane l takes column 4*(l & 7) + (l >> 3): every quarter-warp then reads one phase of
+    // 8 consecutive column groups = 8 consecutive texels for ANY tap column (conflict-free 128-bit loads; with lanes on
+    // consecutive columns the dx = +-1 taps of a quarter-warp straddle two groups of the same phase -> 2-way conflicts),
+    // while the warp as a whole still covers 32 consecutive columns (coalesced gathers / stores, conflict-free scalars).
+    const int tx = (tid & 32) + 4 * (lane & 7) + (lane >> 3), sy = tid / BS_SX;
     const int u = x0 + tx, v0 = y0 + 4 * sy;
     const int rl = 4 * sy;                       // tile row of output 0 (smem row rl+1: planes carry one halo row)
 

@@ -78,6 +78,9 @@ __device__ __forceinline__ void photometric4(const float* __restrict__ xs, const
     float ssum[4], lsum[4];
 #pragma unroll
     for (int ch = 0; ch < 3; ch++) {
+        // NOTE (measured, round 1): running the E[xx] / E[xy] sums as one packed fp32x2 chain (__fadd2_rn, bit-identical)
+        // removed 384 issue slots per thread but changed neither kernel time (0.351 vs 0.353 ms at C2): this phase is
+        // bound by the FP32 pipe itself, where FADD2 costs two passes.  Not kept.
         float sx[4], sxx[4], sxy[4], l1[4];
 #pragma unroll
         for (int dy = 0; dy < 3; dy++) {
@@ -316,7 +319,7 @@ __global__ void __launch_bounds__(NT, MIN_CTAS) fwd_kernel(const FwdParams p, co
         // tile row write 256 contiguous bytes, and the backward's 3x3 taps are bank-conflict-free 128-bit loads.
         // Source 0's texels are stored as they are produced; source 1's wait in registers for the argmin.
         float4* st = nullptr;
-        const size_t st_ch = (size_t)H * 4 * p.Wg;
+        const int st_ch = H * 4 * p.Wg;          // texels per channel map (32-bit offsets: 3*H*4*Wg < 2^31 by check_problem)
         float c1[3][3][4];
         // rows below the image and column groups right of it do not exist in the stash (the backward's TMA zero-fills them)
         const bool row_ok = STASH && v < H && (x0 >> 2) + tx < p.Wg;
