@@ -526,6 +526,7 @@ static int check_problem(const MgvsProblem* p)
         if (p->stash_bytes < stash_bytes(p->B, p->H, p->W, p->n)) return fail(MGVS_EWORKSPACE, "stash too small");
         if ((long long)3 * p->H * 4 * ((p->W + 3) / 4) >= (1ll << 31)) return fail(MGVS_EINVAL, "image too large for the stash's 32-bit texel offsets");
         if (!encode_fn()) return fail(MGVS_ECUDA, "cuTensorMapEncodeTiled unavailable: the stash backward needs TMA");
+        if (!(TW == 64 && TH == 16 && NT == 256)) return fail(MGVS_EUNSUPPORTED, "stash backward is built for the 64x16 tile only (tile-shape experiment build)");
     }
     return MGVS_OK;
 }

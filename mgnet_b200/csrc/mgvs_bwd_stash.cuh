@@ -52,17 +52,30 @@ constexpr int BS_GROUPS = PITCH / 4;                  // 18 column groups per te
 constexpr int BS_TEX = BS_ROWS * PITCH;               // texels per channel map: [row][phase][group]
 constexpr int BS_TILE3_FLOATS = (3 * BS_CH + 31) / 32 * 32;
 constexpr int BS_INV_FLOATS = (BS_CH + 31) / 32 * 32;
-constexpr int BS_SMEM_FLOATS = 3 * BS_TEX * 4 + BS_TILE3_FLOATS + 4 * BS_INV_FLOATS + 8 * 24 + 48 + 4 * MAXN + 8;
+// Two CTAs per SM fit the 196 KB shared-memory carveout (2 x (99,328 + 1 KB reserved)), which leaves 60 instead of
+// 28 KB of L1 for the bilinear gathers; the pose-partial scratch therefore aliases the target tile, which is dead by
+// then.  (Measured: no effect on kernel time at C2/C3/C4 -- the L1 capacity is not what limits the gathers.)
+constexpr int BS_SMEM_FLOATS = 3 * BS_TEX * 4 + BS_TILE3_FLOATS + 4 * BS_INV_FLOATS + 48 + 4 * MAXN + 8;
+static_assert(BS_TILE3_FLOATS >= 8 * 24, "pose-partial scratch aliases the target tile");
 constexpr int BS_SMEM_BYTES = BS_SMEM_FLOATS * 4;
+static_assert(2 * (BS_SMEM_BYTES + 1024) <= 196 * 1024, "stash backward must fit the 196 KB carveout twice");
 static_assert((BS_TEX * 16) % 128 == 0, "channel maps must stay 128-byte aligned for TMA");
 
 namespace tma {
 // 5-D tiled load: box origin (c0..c4) in elements
-__device__ __forceinline__ void load_5d(void* dst, const void* tmap, int c0, int c1, int c2, int c3, int c4, uint64_t* bar)
+// The coefficient texels are read exactly once: L2 evict-first keeps them from displacing the packed sources the
+// bilinear gathers re-read.
+__device__ __forceinline__ uint64_t policy_evict_first()
+{
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ void load_5d(void* dst, const void* tmap, int c0, int c1, int c2, int c3, int c4, uint64_t* bar, uint64_t pol)
 {
     asm volatile(
-        "cp.async.bulk.tensor.5d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5, %6}], [%7];"
-        ::"r"(smem_u32(dst)), "l"(tmap), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4), "r"(smem_u32(bar)) : "memory");
+        "cp.async.bulk.tensor.5d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%2, %3, %4, %5, %6}], [%7], %8;"
+        ::"r"(smem_u32(dst)), "l"(tmap), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4), "r"(smem_u32(bar)), "l"(pol) : "memory");
 }
 }  // namespace tma
 
@@ -133,7 +146,7 @@ __device__ __forceinline__ float signed_const(float cf, float d)
 }
 
 constexpr int BS_SX = 64;                  // thread layout of the stash backward: 64 columns x 4 strips of 4 rows
-static_assert(TW == 64 && TH == 16 && NT == 256, "bwd_stash_kernel assumes a 64x16 tile and 256 threads");
+// (assumes the 64x16 tile / 256 threads of the product build; mgvs_api.cu refuses the stash path otherwise)
 
 template <bool USE_TMA>
 __global__ void __launch_bounds__(NT, MIN_CTAS) bwd_stash_kernel(const __grid_constant__ BwdSParams p, const __grid_constant__ BwdSMaps maps)
@@ -144,8 +157,8 @@ __global__ void __launch_bounds__(NT, MIN_CTAS) bwd_stash_kernel(const __grid_co
     float* sInv = sY + BS_TILE3_FLOATS;                    // [2][BS_ROWS][PITCH] inverse-depth ring
     float* sWx = sInv + 2 * BS_INV_FLOATS;                 // [BS_ROWS][PITCH] masked edge-aware weight of pair (q, q+1), from the forward
     float* sWy = sWx + BS_INV_FLOATS;                      // [BS_ROWS][PITCH] same for pair (q, q+W)
-    float* sRed = sWy + BS_INV_FLOATS;                     // [8 warps][24]
-    float* sCam = sRed + 8 * 24;                           // 48, padded rows (load_cam_padded)
+    float* sRed = sY;                                      // [8 warps][24], after the scale loop only (aliases the dead target tile)
+    float* sCam = sWy + BS_INV_FLOATS;                     // 48, padded rows (load_cam_padded)
     float* sSm = sCam + 48;                                // [n][4]
     uint64_t* sBar = reinterpret_cast<uint64_t*>(sSm + 4 * MAXN);   // [0] target + weights, [1],[2] inverse-depth ring, [3] coefficients
 
@@ -172,9 +185,10 @@ __global__ void __launch_bounds__(NT, MIN_CTAS) bwd_stash_kernel(const __grid_co
     constexpr uint32_t COEF_BYTES = 3 * BS_TEX * 16;
     auto load_coef = [&](int i) {      // thread 0 only: the three channel maps of scale i
         tma::mbar_expect_tx(sBar + 3, COEF_BYTES);
+        const uint64_t pol = tma::policy_evict_first();
 #pragma unroll
         for (int ch = 0; ch < 3; ch++)
-            tma::load_5d(sCo + ch * BS_TEX, &maps.coef, 0, (x0 >> 2) - 1, 0, y0 - 1, (i * p.B + b) * 3 + ch, sBar + 3);
+            tma::load_5d(sCo + ch * BS_TEX, &maps.coef, 0, (x0 >> 2) - 1, 0, y0 - 1, (i * p.B + b) * 3 + ch, sBar + 3, pol);
     };
     auto load_plane_manual = [&](const float* __restrict__ img, float* dst) {     // [H][W] plane -> tile+1, zero outside
         for (int idx = tid; idx < BS_CH; idx += NT) {
@@ -401,6 +415,7 @@ __global__ void __launch_bounds__(NT, MIN_CTAS) bwd_stash_kernel(const __grid_co
     }
 
     // deterministic pose partials: shuffle tree -> smem -> fixed-order sum -> one store per tile
+    __syncthreads();     // sRed aliases sY: every warp is done with the target tile
 #pragma unroll
     for (int s = 0; s < S; s++)
 #pragma unroll

@@ -327,7 +327,7 @@ __global__ void __launch_bounds__(NT, MIN_CTAS) fwd_kernel(const FwdParams p, co
             st = p.stash + ((size_t)i * p.B + b) * 3 * st_ch + (size_t)v * 4 * p.Wg + (x0 >> 2) + tx;
             photometric4<true>(sX + ty * PITCH + XOFF + 4 * tx, ys_t, yst_t, p.alpha, p.oma, lw0,
                                [&](int ch, int k, float a, float bq, float c) {
-                                   if (row_ok) st[ch * st_ch + k * p.Wg] = make_float4(a, bq, c, 1.f);
+                                   if (row_ok) __stcs(st + ch * st_ch + k * p.Wg, make_float4(a, bq, c, 1.f));     // streaming: written once, read once
                                });
             photometric4<true>(sX + FWD_TILE3_FLOATS + ty * PITCH + XOFF + 4 * tx, ys_t, yst_t, p.alpha, p.oma, lw1,
                                [&](int ch, int k, float a, float bq, float c) { c1[ch][0][k] = a; c1[ch][1][k] = bq; c1[ch][2][k] = c; });
@@ -361,7 +361,7 @@ __global__ void __launch_bounds__(NT, MIN_CTAS) fwd_kernel(const FwdParams p, co
                 if (!w0) {
 #pragma unroll
                     for (int ch = 0; ch < 3; ch++)
-                        st[ch * st_ch + k * p.Wg] = make_float4(w1 ? c1[ch][0][k] : 0.f, w1 ? c1[ch][1][k] : 0.f, w1 ? c1[ch][2][k] : 0.f, 0.f);
+                        __stcs(st + ch * st_ch + k * p.Wg, make_float4(w1 ? c1[ch][0][k] : 0.f, w1 ? c1[ch][1][k] : 0.f, w1 ? c1[ch][2][k] : 0.f, 0.f));
                 }
             }
         }

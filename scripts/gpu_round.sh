@@ -15,7 +15,7 @@ if [ "$MODE" = "full" ]; then
   ncu --metrics gpu__time_duration.sum --clock-control none -c 200 --csv --log-file gpurun_out/${TAG}_launches.csv \
       python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-e2e > gpurun_out/${TAG}_ncu_launch.log 2>&1
   # one full capture of each hot kernel (skip warm-up launches)
-  ncu --set full --clock-control none --import-source on -k regex:'fwd_kernel|bwd_kernel' -s 6 -c 2 -f -o gpurun_out/${TAG}_prof \
+  ncu --set full --clock-control none --import-source on -k regex:'fwd_kernel|bwd_' -s 6 -c 2 -f -o gpurun_out/${TAG}_prof \
       python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-e2e > gpurun_out/${TAG}_ncu_full.log 2>&1
 fi
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv | tee gpurun_out/${TAG}_smi.txt
