@@ -291,6 +291,11 @@ __global__ void __launch_bounds__(NT, MIN_CTAS) fwd_kernel(const FwdParams p, co
     const float4* src0 = p.psrc[0] + (size_t)b * pimg;
     const float4* src1 = p.psrc[1] + (size_t)b * pimg;
 
+    // NOTE (measured, round 1): a software pipeline by source -- SSIM(s0, i) || warp(s1, i), then SSIM(s1, i) || warp(s0, i+1),
+    // the two source buffers alternating roles, half of the warps gathering first and half starting with their SSIM strip
+    // -- was bit-identical but SLOWER (C2 forward 0.357 -> 0.379 ms, 0.291 -> 0.320 without the stash): the gather stage
+    // is a latency chain, so warping one source per phase pays that chain twice per scale instead of once.  Overlapping the
+    // warp of BOTH sources of scale i+1 with the SSIM of scale i would need two more source tiles (31 KB) of shared memory.
     for (int i = 0; i < p.n; i++) {
         const float* inv = p.inv[i] + (size_t)b * HW;
         const float* sI = sInv + (i & 1) * FWD_INV_FLOATS;
@@ -305,15 +310,12 @@ __global__ void __launch_bounds__(NT, MIN_CTAS) fwd_kernel(const FwdParams p, co
             tma::mbar_wait(sBar + 1 + (i & 1), (i >> 1) & 1);
         }
         // ---- stage 1: warp both sources at every halo pixel (software pipelined, mgvs_device.cuh) ----
-#ifndef MGVS_SKIP_S1
         warp_tile<1, FWD_ROWS, FWD_CH, USE_TMA>(sX, sX + FWD_TILE3_FLOATS, sI, inv, src0, src1, sCam, x0, y0, H, W, border,
                                                  wm1, hm1, rw, rh, tid);
-#endif
         __syncthreads();
 
         // ---- stage 2: photometric maps, min/argmin, smoothness ----
         float lw0[4], lw1[4];
-#ifndef MGVS_SKIP_S2
         // STASH: coefficient texels (a, b, c, [source == 0]) of this scale, one float4 per (channel, pixel), in the
         // phase-major layout [scale][image][channel][row][u & 3][u >> 2] -- for a fixed output k the 16 threads of a
         // tile row write 256 contiguous bytes, and the backward's 3x3 taps are bank-conflict-free 128-bit loads.
@@ -335,9 +337,6 @@ __global__ void __launch_bounds__(NT, MIN_CTAS) fwd_kernel(const FwdParams p, co
             photometric4<false>(sX + ty * PITCH + XOFF + 4 * tx, ys_t, yst_t, p.alpha, p.oma, lw0, NoEmit());
             photometric4<false>(sX + FWD_TILE3_FLOATS + ty * PITCH + XOFF + 4 * tx, ys_t, yst_t, p.alpha, p.oma, lw1, NoEmit());
         }
-#else
-        for (int k = 0; k < 4; k++) { lw0[k] = sX[ty * PITCH + XOFF + 4 * tx + k]; lw1[k] = sX[FWD_TILE3_FLOATS + ty * PITCH + XOFF + 4 * tx + k]; }
-#endif
         float photo = 0.f;
         unsigned selw = 0;
 #pragma unroll
