@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define MGVS_ABI_VERSION 3
+#define MGVS_ABI_VERSION 4
 #define MGVS_MAX_SCALES 8   /* n: number of inverse-depth maps (reference: 3, mg_net.py:760-764) */
 #define MGVS_NUM_SOURCES 2  /* S: prev, next -- hard-coded in the reference (loss.py:116) */
 
@@ -76,6 +76,15 @@ typedef struct MgvsProblem {
                                    issue-bound, HBM is idle).  NULL keeps the recompute backward (nothing but `sel`
                                    and the sums carried over).  Must stay untouched between forward and backward. */
     size_t stash_bytes;
+    int inv_height[MGVS_MAX_SCALES]; /* fused head-side upsample: all zero = inv_depth[i] are full resolution */
+    int inv_width[MGVS_MAX_SCALES];  /* (the reference's contract).  Otherwise inv_depth[i] is the depth head's low-resolution
+                                   map [B,1,inv_height[i],inv_width[i]] BEFORE its F.interpolate(scale_factor=stride,
+                                   mode="bilinear", align_corners=True) (mg_net.py:803-806), with H = h*s and W = w*s for an
+                                   integer s: the kernels apply that upsample themselves, bit-identically to ATen's CPU
+                                   kernel, and mgvs_backward returns grad_inv[i] at the LOW resolution (the adjoint of the
+                                   upsample is applied in fixed order: deterministic, unlike ATen's atomics on CUDA).  All
+                                   maps must be low resolution or none; needs the stash (mgvs_stash_bytes_ex(..., 1)),
+                                   W % 4 == 0 and 16-byte aligned image tensors. */
 } MgvsProblem;
 
 int mgvs_abi_version(void);
@@ -88,6 +97,8 @@ size_t mgvs_workspace_bytes_ex(int B, int H, int W, int n, int image_dtype);
 
 /* Size of the optional coefficient stash (MgvsProblem.stash). */
 size_t mgvs_stash_bytes(int B, int H, int W, int n);
+/* Same with fused_upsample != 0: room for the full-resolution depth gradients the upsample adjoint consumes. */
+size_t mgvs_stash_bytes_ex(int B, int H, int W, int n, int fused_upsample);
 
 /* Number of doubles in the partial-sum vector: 3n+3 =
  *   [0,n)     sum over masked pixels of the per-pixel minimum photometric loss, per scale (loss.py:245)

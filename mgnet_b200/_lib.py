@@ -15,7 +15,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _CSRC = os.path.join(_HERE, "csrc")
 LIB_PATH = os.environ.get("MGVS_LIB_PATH") or os.path.join(_HERE, "libmgvs.so")   # override: kernel-variant experiments only
 MAX_SCALES = 8
-ABI_VERSION = 3
+ABI_VERSION = 4
 IMAGE_F32, IMAGE_U8 = 0, 1
 NUM_SOURCES = 2
 
@@ -41,6 +41,7 @@ class MgvsProblem(ctypes.Structure):
         ("workspace", ctypes.c_void_p), ("workspace_bytes", ctypes.c_size_t),
         ("image_dtype", ctypes.c_int),
         ("stash", ctypes.c_void_p), ("stash_bytes", ctypes.c_size_t),
+        ("inv_height", ctypes.c_int * MAX_SCALES), ("inv_width", ctypes.c_int * MAX_SCALES),
     ]
 
 
@@ -104,6 +105,8 @@ def lib():
     L.mgvs_workspace_bytes_ex.argtypes = [ci, ci, ci, ci, ci]
     L.mgvs_stash_bytes.restype = ctypes.c_size_t
     L.mgvs_stash_bytes.argtypes = [ci, ci, ci, ci]
+    L.mgvs_stash_bytes_ex.restype = ctypes.c_size_t
+    L.mgvs_stash_bytes_ex.argtypes = [ci, ci, ci, ci, ci]
     L.mgvs_forward.restype = ci
     L.mgvs_forward.argtypes = [PP, vp, vp, vp]
     L.mgvs_forward_losses.restype = ci
@@ -127,7 +130,7 @@ def lib():
 
 
 EXPORTED_SYMBOLS = (
-    "mgvs_abi_version", "mgvs_last_error", "mgvs_num_sums", "mgvs_workspace_bytes", "mgvs_workspace_bytes_ex", "mgvs_stash_bytes", "mgvs_forward", "mgvs_forward_losses",
+    "mgvs_abi_version", "mgvs_last_error", "mgvs_num_sums", "mgvs_workspace_bytes", "mgvs_workspace_bytes_ex", "mgvs_stash_bytes", "mgvs_stash_bytes_ex", "mgvs_forward", "mgvs_forward_losses",
     "mgvs_finalize", "mgvs_backward", "mgvs_view_synthesis", "mgvs_reconstruct", "mgvs_project", "mgvs_test_div",
 )
 

@@ -74,16 +74,34 @@ static bool make_stash_map(TmaDesc* out, const void* base, int planes, int H, in
 }
 // stash = coefficient texels [n][B][3][H][4][Wg] float4, then the two masked edge-aware weight planes [2B][H][4*Wg] floats
 static size_t stash_texel_bytes(int B, int H, int W, int n) { return align256((size_t)n * B * 3 * H * 4 * ((W + 3) / 4) * sizeof(float4)); }
-static size_t stash_bytes(int B, int H, int W, int n) { return stash_texel_bytes(B, H, W, n) + align256((size_t)2 * B * H * 4 * ((W + 3) / 4) * sizeof(float)); }
+static size_t stash_weight_bytes(int B, int H, int W) { return align256((size_t)2 * B * H * 4 * ((W + 3) / 4) * sizeof(float)); }
+// fused upsample: + the n full-resolution depth-gradient maps the upsample adjoint reads
+static size_t stash_bytes(int B, int H, int W, int n, bool lowres = false)
+{
+    return stash_texel_bytes(B, H, W, n) + stash_weight_bytes(B, H, W) + (lowres ? (size_t)n * align256((size_t)B * H * W * sizeof(float)) : 0);
+}
+static int lowres_mode(const MgvsProblem* p)   // 0 = full resolution, 1 = all maps low resolution, -1 = invalid
+{
+    int cnt = 0;
+    for (int i = 0; i < p->n; i++) {
+        const int h = p->inv_height[i], w = p->inv_width[i];
+        if (h == 0 && w == 0) continue;
+        if (h < 1 || w < 1 || p->H % h != 0 || p->W % w != 0 || p->H / h != p->W / w) return -1;
+        cnt++;
+    }
+    return cnt == 0 ? 0 : (cnt == p->n ? 1 : -1);
+}
 
+static int lowres_mode(const MgvsProblem* p);
 // TMA needs 16-byte aligned bases and row strides (W % 4 == 0); otherwise the kernels use their manual loaders.
 static bool tma_eligible(const MgvsProblem* p, const float* tgt, const float* src0, const float* src1)
 {
     if (p->W % 4 != 0) return false;
     auto al = [](const void* q) { return ((uintptr_t)q & 15) == 0; };
     if (!al(tgt) || !al(src0) || !al(src1)) return false;
-    for (int i = 0; i < p->n; i++)
-        if (!al(p->inv_depth[i])) return false;
+    if (!lowres_mode(p))
+        for (int i = 0; i < p->n; i++)
+            if (!al(p->inv_depth[i])) return false;
     return encode_fn() != nullptr;
 }
 
@@ -507,6 +525,42 @@ __global__ void project_kernel(int B, int H, int W, const float* __restrict__ X,
     coords[idx * 2 + 1] = __fadd_rn(__fdiv_rn(__fadd_rn(ay, ay), (float)(H - 1)), -1.0f);
 }
 
+// ---------------------------------------------------------------------------------------------
+// Adjoint of the fused head-side upsample (F.interpolate bilinear, align_corners=True): one warp per low-resolution
+// pixel gathers weight * full-resolution gradient over its support with the forward's own index / weight arithmetic
+// (upsample_axis) and reduces in fixed order -- deterministic, where ATen's CUDA backward uses float atomics.
+__global__ void __launch_bounds__(256) upsample_adjoint_kernel(int B, int H, int W, int h, int w, float ry, float rx,
+                                                               const float* __restrict__ gfull, float* __restrict__ glow)
+{
+    const int lane = threadIdx.x & 31;
+    const long long wid = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (wid >= (long long)B * h * w) return;
+    const int px = (int)(wid % w), py = (int)((wid / w) % h), b = (int)(wid / ((long long)w * h));
+    // generous bounds of the support (rows whose i0 or i1 can equal py), exact membership is tested per element
+    const int sy = H / h, sx = W / w;
+    const int vlo = max(0, (py - 1) * sy - sy), vhi = min(H - 1, (py + 1) * sy + sy);
+    const int ulo = max(0, (px - 1) * sx - sx), uhi = min(W - 1, (px + 1) * sx + sx);
+    const int ncol = uhi - ulo + 1;
+    double acc = 0.0;
+    const float* g = gfull + (size_t)b * H * W;
+    for (int v = vlo; v <= vhi; v++) {
+        int y0, y1; float ly0, ly1;
+        upsample_axis(ry, v, h, y0, y1, ly0, ly1);
+        const float wy = (y0 == py ? ly0 : 0.f) + (y1 == py ? ly1 : 0.f);
+        if (wy == 0.f) continue;      // warp-uniform
+        for (int c = lane; c < ncol; c += 32) {
+            const int u = ulo + c;
+            int x0, x1; float lx0, lx1;
+            upsample_axis(rx, u, w, x0, x1, lx0, lx1);
+            const float wx = (x0 == px ? lx0 : 0.f) + (x1 == px ? lx1 : 0.f);
+            if (wx != 0.f) acc += (double)(wy * wx) * (double)__ldg(g + (size_t)v * W + u);
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane == 0) glow[((size_t)b * h + py) * w + px] = (float)acc;
+}
+
 static int check_problem(const MgvsProblem* p)
 {
     if (!p) return fail(MGVS_EINVAL, "null problem");
@@ -521,9 +575,12 @@ static int check_problem(const MgvsProblem* p)
     if (!p->workspace || ((uintptr_t)p->workspace & 255)) return fail(MGVS_EINVAL, "workspace null or not 256-byte aligned");
     if (p->image_dtype != MGVS_IMAGE_F32 && p->image_dtype != MGVS_IMAGE_U8) return fail(MGVS_EINVAL, "image_dtype must be MGVS_IMAGE_F32 or MGVS_IMAGE_U8");
     if (p->workspace_bytes < make_layout(p->B, p->H, p->W, p->n, p->image_dtype).total) return fail(MGVS_EWORKSPACE, "workspace too small");
+    const int lowres = lowres_mode(p);
+    if (lowres < 0) return fail(MGVS_EINVAL, "inv_height/inv_width: all maps must be full resolution (0) or all low resolution with H = h*s, W = w*s");
+    if (lowres && (p->W % 4 != 0)) return fail(MGVS_EUNSUPPORTED, "fused upsample needs W % 4 == 0");
     if (p->stash) {
         if ((uintptr_t)p->stash & 255) return fail(MGVS_EINVAL, "stash not 256-byte aligned");
-        if (p->stash_bytes < stash_bytes(p->B, p->H, p->W, p->n)) return fail(MGVS_EWORKSPACE, "stash too small");
+        if (p->stash_bytes < stash_bytes(p->B, p->H, p->W, p->n, lowres != 0)) return fail(MGVS_EWORKSPACE, "stash too small");
         if ((long long)3 * p->H * 4 * ((p->W + 3) / 4) >= (1ll << 31)) return fail(MGVS_EINVAL, "image too large for the stash's 32-bit texel offsets");
         if (!encode_fn()) return fail(MGVS_ECUDA, "cuTensorMapEncodeTiled unavailable: the stash backward needs TMA");
         if (!(TW == 64 && TH == 16 && NT == 256)) return fail(MGVS_EUNSUPPORTED, "stash backward is built for the 64x16 tile only (tile-shape experiment build)");
@@ -573,11 +630,12 @@ size_t mgvs_workspace_bytes_ex(int B, int H, int W, int n, int image_dtype)
     return make_layout(B, H, W, n, image_dtype).total;
 }
 size_t mgvs_workspace_bytes(int B, int H, int W, int n) { return mgvs_workspace_bytes_ex(B, H, W, n, MGVS_IMAGE_F32); }
-size_t mgvs_stash_bytes(int B, int H, int W, int n)
+size_t mgvs_stash_bytes_ex(int B, int H, int W, int n, int fused_upsample)
 {
     if (B < 1 || H < 1 || W < 1 || n < 1 || n > MGVS_MAX_SCALES) return 0;
-    return stash_bytes(B, H, W, n);
+    return stash_bytes(B, H, W, n, fused_upsample != 0);
 }
+size_t mgvs_stash_bytes(int B, int H, int W, int n) { return mgvs_stash_bytes_ex(B, H, W, n, 0); }
 
 int mgvs_forward_losses(const MgvsProblem* p, unsigned char* sel, double* sums, float* losses, void* cuda_stream)
 {
@@ -617,12 +675,20 @@ int mgvs_forward_losses(const MgvsProblem* p, unsigned char* sel, double* sums, 
     fp.alpha = p->ssim_weight; fp.oma = p->one_minus_ssim_weight;
     fp.tiles_x = L.tiles_x; fp.tiles_y = L.tiles_y;
     FwdMaps maps;
+    const int lowres = lowres_mode(p);
     bool use_tma = tma_eligible(p, tgt_f, src_f[0], src_f[1]);
     if (use_tma) {
         use_tma = make_map(&maps.tgt, tgt_f, 3 * p->B, p->H, p->W, FWD_ROWS, 3) &&
                   make_map(&maps.src[0], src_f[0], 3 * p->B, p->H, p->W, FWD_ROWS, 3) &&
                   make_map(&maps.src[1], src_f[1], 3 * p->B, p->H, p->W, FWD_ROWS, 3);
-        for (int i = 0; i < p->n && use_tma; i++) use_tma = make_map(&maps.inv[i], p->inv_depth[i], p->B, p->H, p->W, FWD_ROWS, 1);
+        for (int i = 0; i < p->n && use_tma && !lowres; i++) use_tma = make_map(&maps.inv[i], p->inv_depth[i], p->B, p->H, p->W, FWD_ROWS, 1);
+    }
+    if (lowres && !use_tma) return fail(MGVS_EUNSUPPORTED, "fused upsample needs 16-byte aligned image tensors (TMA path)");
+    fp.lowres = lowres;
+    for (int i = 0; i < p->n && lowres; i++) {
+        fp.inv_h[i] = p->inv_height[i]; fp.inv_w[i] = p->inv_width[i];
+        fp.inv_ry[i] = p->H > 1 ? (float)((double)(p->inv_height[i] - 1) / (double)(p->H - 1)) : 0.f;   // ATen: (in-1)/(out-1) in fp32
+        fp.inv_rx[i] = p->W > 1 ? (float)((double)(p->inv_width[i] - 1) / (double)(p->W - 1)) : 0.f;
     }
     fp.early_wait = u8 ? 1 : 0;
     if (!use_tma) memset(&maps, 0, sizeof(maps));
@@ -659,6 +725,7 @@ int mgvs_backward(const MgvsProblem* p, const unsigned char* sel, const double* 
     int rc = check_problem(p);
     if (rc) return rc;
     if (!sel || !sums || !g_losses || !grad_inv || !grad_poses) return fail(MGVS_EINVAL, "null argument");
+    if (lowres_mode(p) && !p->stash) return fail(MGVS_EUNSUPPORTED, "fused upsample: the backward needs the coefficient stash (MgvsProblem.stash, mgvs_stash_bytes_ex(..., 1))");
     cudaStream_t st = (cudaStream_t)cuda_stream;
     Layout L = make_layout(p->B, p->H, p->W, p->n, p->image_dtype);
     char* ws = (char*)p->workspace;
@@ -672,10 +739,21 @@ int mgvs_backward(const MgvsProblem* p, const unsigned char* sel, const double* 
         memset(&sp, 0, sizeof(sp));
         sp.B = p->B; sp.H = p->H; sp.W = p->W; sp.n = p->n; sp.automask = p->automask;
         sp.tgt = tgt_f;
+        const int lowres = lowres_mode(p);
+        // fused upsample: the kernel writes full-resolution gradients into the stash tail, the adjoint kernel folds them
+        // down into the caller's low-resolution grad_inv[i]
+        char* gfull = (char*)p->stash + stash_texel_bytes(p->B, p->H, p->W, p->n) + stash_weight_bytes(p->B, p->H, p->W);
+        const size_t gfull_stride = align256((size_t)p->B * p->H * p->W * sizeof(float));
+        sp.lowres = lowres;
         for (int i = 0; i < p->n; i++) {
             sp.inv[i] = p->inv_depth[i];
             if (!grad_inv[i]) return fail(MGVS_EINVAL, "null grad_inv pointer");
-            sp.grad_inv[i] = grad_inv[i];
+            sp.grad_inv[i] = lowres ? (float*)(gfull + (size_t)i * gfull_stride) : grad_inv[i];
+            if (lowres) {
+                sp.inv_h[i] = p->inv_height[i]; sp.inv_w[i] = p->inv_width[i];
+                sp.inv_ry[i] = p->H > 1 ? (float)((double)(p->inv_height[i] - 1) / (double)(p->H - 1)) : 0.f;
+                sp.inv_rx[i] = p->W > 1 ? (float)((double)(p->inv_width[i] - 1) / (double)(p->W - 1)) : 0.f;
+            }
         }
         sp.mask = p->mask; sp.cams = (const Cam*)(ws + L.cams); sp.sel = sel; sp.sums = sums;
         sp.psrc[0] = (const float4*)(ws + L.packed[0]); sp.psrc[1] = (const float4*)(ws + L.packed[1]);
@@ -693,12 +771,17 @@ int mgvs_backward(const MgvsProblem* p, const unsigned char* sel, const double* 
         bool tma_img = tma_eligible(p, tgt_f, src_f[0], src_f[1]);
         if (tma_img) {
             tma_img = make_map(&smaps.tgt, tgt_f, 3 * p->B, p->H, p->W, BS_ROWS, 3);
-            for (int i = 0; i < p->n && tma_img; i++) tma_img = make_map(&smaps.inv[i], p->inv_depth[i], p->B, p->H, p->W, BS_ROWS, 1);
+            for (int i = 0; i < p->n && tma_img && !lowres; i++) tma_img = make_map(&smaps.inv[i], p->inv_depth[i], p->B, p->H, p->W, BS_ROWS, 1);
         }
         void (*kern)(BwdSParams, BwdSMaps) = tma_img ? bwd_stash_kernel<true> : bwd_stash_kernel<false>;
         cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, BS_SMEM_BYTES);
         kern<<<L.tiles, NT, BS_SMEM_BYTES, st>>>(sp, smaps);
         pose_reduce_kernel<<<p->B * S, 128, 0, st>>>(L.tiles_x * L.tiles_y, sp.pose_partials, p->poses, grad_poses);
+        for (int i = 0; i < p->n && lowres; i++) {
+            const long long warps = (long long)p->B * sp.inv_h[i] * sp.inv_w[i];
+            upsample_adjoint_kernel<<<(unsigned)((warps * 32 + 255) / 256), 256, 0, st>>>(p->B, p->H, p->W, sp.inv_h[i], sp.inv_w[i], sp.inv_ry[i],
+                                                                                         sp.inv_rx[i], sp.grad_inv[i], grad_inv[i]);
+        }
         return check_launch("mgvs_backward (stash)");
     }
     BwdParams bp;

@@ -41,6 +41,9 @@ struct BwdSParams {
     float* pose_partials;         // [tiles][S*12]
     float alpha, oma, photo_w, smooth_w;
     int tiles_x, tiles_y;
+    int lowres;                   // fused head-side upsample: inv[i] are low-resolution maps (see FwdParams)
+    int inv_h[MAXN], inv_w[MAXN];
+    float inv_ry[MAXN], inv_rx[MAXN];
 };
 struct BwdSMaps {
     TmaDesc tgt, inv[MAXN], coef, wgt;     // wgt: the two masked edge-aware weight planes [2B][H][4*Wg] of the stash
@@ -197,6 +200,17 @@ __global__ void __launch_bounds__(NT, MIN_CTAS) bwd_stash_kernel(const __grid_co
             dst[idx] = (vv >= 0 && vv < H && uu >= 0 && uu < W) ? __ldg(img + (size_t)vv * W + uu) : 0.f;
         }
     };
+    // inverse-depth tiles: TMA from the full-resolution maps, or filled by hand (manual-loader build, or fused upsample
+    // of the head's low-resolution maps)
+    const bool inv_tma = USE_TMA && !p.lowres;
+    auto fill_inv = [&](int i, float* dst) {
+        if (p.lowres) {
+            LowRes lr = {p.inv[i] + (size_t)b * p.inv_h[i] * p.inv_w[i], p.inv_h[i], p.inv_w[i], p.inv_ry[i], p.inv_rx[i]};
+            fill_inv_tile_lowres<1, BS_ROWS>(dst, lr, x0, y0, H, W, tid);
+        } else {
+            load_plane_manual(p.inv[i] + (size_t)b * HW, dst);
+        }
+    };
     if (tid == 0) {
         tma::mbar_init(sBar + 0, 1); tma::mbar_init(sBar + 1, 1); tma::mbar_init(sBar + 2, 1); tma::mbar_init(sBar + 3, 1);
         tma::fence_barrier_init();
@@ -204,8 +218,8 @@ __global__ void __launch_bounds__(NT, MIN_CTAS) bwd_stash_kernel(const __grid_co
         tma::mbar_expect_tx(sBar + 0, (USE_TMA ? 3 : 0) * BS_CH * 4 + 2 * BS_CH * 4);
         tma::load_3d(sWx, &maps.wgt, x0 - XOFF, y0 - 1, 2 * b, sBar + 0);
         tma::load_3d(sWy, &maps.wgt, x0 - XOFF, y0 - 1, 2 * b + 1, sBar + 0);
-        if (USE_TMA) {
-            tma::load_3d(sY, &maps.tgt, x0 - XOFF, y0 - 1, 3 * b, sBar + 0);
+        if (USE_TMA) tma::load_3d(sY, &maps.tgt, x0 - XOFF, y0 - 1, 3 * b, sBar + 0);
+        if (inv_tma) {
             tma::mbar_expect_tx(sBar + 1, BS_CH * 4);
             tma::load_3d(sInv, &maps.inv[0], x0 - XOFF, y0 - 1, b, sBar + 1);
         }
@@ -230,8 +244,8 @@ __global__ void __launch_bounds__(NT, MIN_CTAS) bwd_stash_kernel(const __grid_co
     if (!USE_TMA) {
 #pragma unroll 1
         for (int ch = 0; ch < 3; ch++) load_plane_manual(p.tgt + ((size_t)b * 3 + ch) * HW, sY + ch * BS_CH);
-        load_plane_manual(p.inv[0] + (size_t)b * HW, sInv);
     }
+    if (!inv_tma) fill_inv(0, sInv);
     __syncthreads();                 // barrier init, camera table, smoothness constants (and manual tiles) visible
     tma::mbar_wait(sBar + 0, 0);
 
@@ -282,7 +296,7 @@ __global__ void __launch_bounds__(NT, MIN_CTAS) bwd_stash_kernel(const __grid_co
 #pragma unroll
         for (int k = 0; k < 4; k++)
             if ((valid >> k) & 1u) selq |= (unsigned)sel[(size_t)(v0 + k) * W + u] << (8 * k);
-        if (USE_TMA) tma::mbar_wait(sBar + 1 + (i & 1), (i >> 1) & 1);
+        if (inv_tma) tma::mbar_wait(sBar + 1 + (i & 1), (i >> 1) & 1);
 
         // ---- smoothness gradient (App. B-6): d/dinv of sum m*w*|inv_p - inv_q| / (N*c) plus the mean term ----
         float ginv[4];
@@ -325,13 +339,13 @@ __global__ void __launch_bounds__(NT, MIN_CTAS) bwd_stash_kernel(const __grid_co
                 if (i + 1 < p.n) {
                     if (tid == 0) {
                         tma::fence_proxy_async();
-                        if (USE_TMA) {
+                        if (inv_tma) {
                             tma::mbar_expect_tx(sBar + 1 + ((i + 1) & 1), BS_CH * 4);
                             tma::load_3d(sInv + ((i + 1) & 1) * BS_INV_FLOATS, &maps.inv[i + 1], x0 - XOFF, y0 - 1, b, sBar + 1 + ((i + 1) & 1));
                         }
                         load_coef(i + 1);
                     }
-                    if (!USE_TMA) load_plane_manual(p.inv[i + 1] + (size_t)b * HW, sInv + ((i + 1) & 1) * BS_INV_FLOATS);
+                    if (!inv_tma) fill_inv(i + 1, sInv + ((i + 1) & 1) * BS_INV_FLOATS);
                 }
             }
 
@@ -411,7 +425,7 @@ __global__ void __launch_bounds__(NT, MIN_CTAS) bwd_stash_kernel(const __grid_co
 #pragma unroll
         for (int k = 0; k < 4; k++)
             if ((valid >> k) & 1u) p.grad_inv[i][(size_t)b * HW + (size_t)(v0 + k) * W + u] = ginv[k];
-        if (!USE_TMA) __syncthreads();     // manually loaded inverse-depth tile of the next scale visible
+        if (!inv_tma) __syncthreads();     // hand-filled inverse-depth tile of the next scale visible
     }
 
     // deterministic pose partials: shuffle tree -> smem -> fixed-order sum -> one store per tile

@@ -30,6 +30,7 @@ class MultiViewPhotometricLoss(nn.Module):
         process_group=None,
         ddp_grad_scale=False,
         backward="stash",
+        fuse_upsample=False,
     ):
         super().__init__()
         self.n = None
@@ -41,6 +42,7 @@ class MultiViewPhotometricLoss(nn.Module):
         self.padding_mode = padding_mode
         self.process_group = process_group
         self.ddp_grad_scale = ddp_grad_scale
+        self.fuse_upsample = fuse_upsample   # predictions["depth"] are the head's low-resolution maps; see ops.LossConfig
         self.backward = backward     # "stash" (fast, +48 B/px/scale of scratch) or "recompute" (lean memory), see ops.LossConfig
         self.last_selection = None   # uint8 [n,B,H,W] argmin of the most recent forward (new side output)
         # same assertion as the reference (loss.py:106-109)
@@ -68,6 +70,7 @@ class MultiViewPhotometricLoss(nn.Module):
             process_group=self.process_group,
             ddp_grad_scale=bool(self.ddp_grad_scale),
             backward=self.backward,
+            fuse_upsample=bool(self.fuse_upsample),
         )
 
     def forward(self, predictions, targets):

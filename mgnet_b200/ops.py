@@ -40,6 +40,11 @@ class LossConfig:
     process_group: object = None      # torch.distributed group for the partial-sum all-reduce (None = local)
     ddp_grad_scale: bool = False      # multiply local grads by world size so DDP's 1/G averaging yields the
                                       # full-batch gradient; only with process_group
+    fuse_upsample: bool = False       # predictions["depth"][i] are the depth head's LOW-resolution maps
+                                      # [B,1,H/s,W/s] (after sigmoid()/0.5, before its F.interpolate(scale_factor=s,
+                                      # mode="bilinear", align_corners=True), mg_net.py:803-806,823); the kernels upsample on
+                                      # the fly (bit-identical to ATen's CPU kernel) and return low-resolution gradients
+                                      # through a deterministic adjoint.  Needs backward="stash".
     backward: str = "stash"           # "stash": the forward also writes the SSIM-adjoint coefficient texels of the
                                       # selected source (48 B/px/scale) and the backward consumes them (fastest);
                                       # "recompute": nothing but the uint8 selection is carried over and the backward
@@ -98,6 +103,10 @@ def _fill_problem(prob, cfg, tgt, prev, nxt, inv, camera, poses, mask, ws, stash
     prob.workspace_bytes = ws.numel()
     prob.stash = stash.data_ptr() if stash is not None else None
     prob.stash_bytes = stash.numel() if stash is not None else 0
+    for i, d in enumerate(inv):
+        lowres = tuple(d.shape[-2:]) != (H, W)
+        prob.inv_height[i] = d.shape[-2] if lowres else 0
+        prob.inv_width[i] = d.shape[-1] if lowres else 0
 
 
 class _ViewSynthesisLoss(torch.autograd.Function):
@@ -122,7 +131,21 @@ class _ViewSynthesisLoss(torch.autograd.Function):
         if not (tgt.dtype == prev.dtype == nxt.dtype):
             raise TypeError("image_orig, image_prev_orig and image_next_orig must share one dtype (float32 or uint8)")
         img_dtype = _lib.IMAGE_U8 if tgt.dtype == torch.uint8 else _lib.IMAGE_F32
-        inv = [_require_cuda_f32(d, "depth[%d]" % i, (B, 1, H, W)) for i, d in enumerate(inv)]
+        if cfg.fuse_upsample:
+            if cfg.backward != "stash":
+                raise NotImplementedError("fuse_upsample needs backward='stash'")
+            checked = []
+            for i, d in enumerate(inv):
+                d = _require_cuda_f32(d, "depth[%d]" % i)
+                if d.dim() != 4 or d.shape[0] != B or d.shape[1] != 1:
+                    raise ValueError("depth[%d] must be [B,1,h,w]" % i)
+                h, w = d.shape[-2:]
+                if h < 1 or w < 1 or H % h or W % w or H // h != W // w or (h, w) == (H, W):
+                    raise ValueError("fuse_upsample: depth[%d] is %dx%d, expected the image size %dx%d divided by one integer stride > 1" % (i, h, w, H, W))
+                checked.append(d)
+            inv = checked
+        else:
+            inv = [_require_cuda_f32(d, "depth[%d]" % i, (B, 1, H, W)) for i, d in enumerate(inv)]
         poses = _require_cuda_f32(poses, "poses", (B, 2, 6))
         if camera.dim() != 3 or camera.shape[0] != B or camera.shape[1] < 3 or camera.shape[2] < 3:
             raise ValueError("camera_matrix must be [B,>=3,>=3]")
@@ -142,7 +165,7 @@ class _ViewSynthesisLoss(torch.autograd.Function):
         want_stash = cfg.backward == "stash" and any(ctx.needs_input_grad[i] for i in (1,) + tuple(range(7, 7 + n)))
         with torch.cuda.device(dev):
             ws = torch.empty(int(L.mgvs_workspace_bytes_ex(B, H, W, n, img_dtype)), dtype=torch.uint8, device=dev)
-            stash = torch.empty(int(L.mgvs_stash_bytes(B, H, W, n)), dtype=torch.uint8, device=dev) if want_stash else None
+            stash = torch.empty(int(L.mgvs_stash_bytes_ex(B, H, W, n, int(cfg.fuse_upsample))), dtype=torch.uint8, device=dev) if want_stash else None
             sel = torch.empty((n, B, H, W), dtype=torch.uint8, device=dev)
             sums = torch.empty(3 * n + 3, dtype=torch.float64, device=dev)
             losses = torch.empty(2, dtype=torch.float32, device=dev)
@@ -202,7 +225,7 @@ class _ViewSynthesisLoss(torch.autograd.Function):
             stream = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
             _lib.check(L.mgvs_backward(ctypes.byref(prob), sel.data_ptr(), sums.data_ptr(), g.data_ptr(), arr,
                                        gp.data_ptr(), stream), "mgvs_backward")
-            launch_counter.n += BWD_LAUNCHES
+            launch_counter.n += BWD_LAUNCHES + (len(inv) if ctx.cfg.fuse_upsample else 0)   # + upsample_adjoint_kernel per scale
         ctx.stash = None
         return (None, gp, None, None, None, None, None) + tuple(grads)
 

@@ -93,6 +93,44 @@ def main():
                                                   float(res["loss_photometric"]), float(res["loss_smoothness"])))
 
 
+def make_fused_upsample():
+    """SURVEY 8f-1 fixture: the depth head's low-resolution maps (strides 8/16/32), upsampled with the head's own
+    F.interpolate(scale_factor=stride, mode="bilinear", align_corners=True) (mg_net.py:803-806) and fed to the
+    unmodified reference loss; gradients are chained back through the interpolate to the low-resolution maps.
+    File name starts with "fused_" so the full-resolution tests skip it."""
+    import torch.nn.functional as F
+    B, H, W, strides = 2, 64, 128, (8, 16, 32)
+    pred, tgt = make_inputs(B=B, H=H, W=W, n=len(strides), seed=8, noise=0.2)
+    g = torch.Generator(device="cpu").manual_seed(8080)
+    lows = [(0.05 + 1.9 * torch.rand(B, 1, H // s, W // s, generator=g)).contiguous() for s in strides]
+    leaves = [lo.clone().requires_grad_(True) for lo in lows]
+    fulls = [F.interpolate(x, scale_factor=s, mode="bilinear", align_corners=True) for x, s in zip(leaves, strides)]
+    hp = dict(ref_loader.DEFAULT_HP)
+    res = ref_loader.run_reference({"depth": [f.detach() for f in fulls], "poses": pred["poses"]}, tgt, hp=hp,
+                                   want_grads=True, want_intermediates=True)
+    out = {
+        "in_image_orig": tgt["image_orig"].numpy(), "in_image_prev_orig": tgt["image_prev_orig"].numpy(),
+        "in_image_next_orig": tgt["image_next_orig"].numpy(), "in_camera_matrix": tgt["camera_matrix"].numpy(),
+        "in_poses": pred["poses"].numpy(), "in_reprojection_mask": tgt["reprojection_mask"].numpy(),
+        "hp_ssim_loss_weight": np.float64(hp["ssim_loss_weight"]), "hp_photometric_loss_weight": np.float64(hp["photometric_loss_weight"]),
+        "hp_smoothing_loss_weight": np.float64(hp["smoothing_loss_weight"]), "hp_automask_loss": np.bool_(hp["automask_loss"]),
+        "loss_photometric": res["loss_photometric"], "loss_smoothness": res["loss_smoothness"], "grad_poses": res["grad_poses"],
+    }
+    for i, (leaf, full) in enumerate(zip(leaves, fulls)):
+        full.backward(torch.from_numpy(res["grad_depth_%d" % i]))
+        out["in_depth_%d" % i] = lows[i].numpy()                 # LOW resolution
+        out["grad_depth_%d" % i] = leaf.grad.numpy()             # LOW resolution
+        out["sel_%d" % i] = res["sel_%d" % i]
+    path = os.path.join(HERE, "fused_upsample_n3.npz")
+    np.savez_compressed(path, **out)
+    print("%-20s %7.1f KB  Lp=%.8f Ls=%.8e" % ("fused_upsample_n3", os.path.getsize(path) / 1024.0,
+                                              float(res["loss_photometric"]), float(res["loss_smoothness"])))
+
+
 if __name__ == "__main__":
     torch.set_num_threads(1)   # the reference on CPU is thread-count independent (SURVEY App. A); be safe
-    main()
+    if len(sys.argv) > 1 and sys.argv[1] == "fused":
+        make_fused_upsample()      # leaves the other (committed) fixtures untouched
+    else:
+        main()
+        make_fused_upsample()

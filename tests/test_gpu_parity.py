@@ -53,7 +53,7 @@ def test_library_loaded_is_in_tree():
     _dev()
     from mgnet_b200 import _lib
     L = _lib.lib()
-    assert L.mgvs_abi_version() == 3
+    assert L.mgvs_abi_version() == 4
     assert _lib.LIB_PATH.endswith("mgnet_b200/libmgvs.so")
 
 
