@@ -78,7 +78,9 @@ static size_t stash_weight_bytes(int B, int H, int W) { return align256((size_t)
 // fused upsample: + the n full-resolution depth-gradient maps the upsample adjoint reads
 static size_t stash_bytes(int B, int H, int W, int n, bool lowres = false)
 {
-    return stash_texel_bytes(B, H, W, n) + stash_weight_bytes(B, H, W) + (lowres ? (size_t)n * align256((size_t)B * H * W * sizeof(float)) : 0);
+    // + one [B][H][W/2] scratch for the separable adjoint (any stride >= 2)
+    return stash_texel_bytes(B, H, W, n) + stash_weight_bytes(B, H, W) +
+           (lowres ? (size_t)n * align256((size_t)B * H * W * sizeof(float)) + align256((size_t)B * H * ((W + 1) / 2) * sizeof(float)) : 0);
 }
 static int lowres_mode(const MgvsProblem* p)   // 0 = full resolution, 1 = all maps low resolution, -1 = invalid
 {
@@ -526,39 +528,73 @@ __global__ void project_kernel(int B, int H, int W, const float* __restrict__ X,
 }
 
 // ---------------------------------------------------------------------------------------------
-// Adjoint of the fused head-side upsample (F.interpolate bilinear, align_corners=True): one warp per low-resolution
-// pixel gathers weight * full-resolution gradient over its support with the forward's own index / weight arithmetic
-// (upsample_axis) and reduces in fixed order -- deterministic, where ATen's CUDA backward uses float atomics.
-__global__ void __launch_bounds__(256) upsample_adjoint_kernel(int B, int H, int W, int h, int w, float ry, float rx,
-                                                               const float* __restrict__ gfull, float* __restrict__ glow)
+// Adjoint of the fused head-side upsample (F.interpolate bilinear, align_corners=True), separable and in fixed order
+// (deterministic, where ATen's CUDA backward scatters with float atomics -- 0.5 ms per map at C2):
+//   pass 1  T[b, v, px]   = sum_u wx(u, px) * g[b, v, u]     one thread per (row, low-res column), contiguous walk over u
+//   pass 2  out[b, py, px] = sum_v wy(v, py) * T[b, v, px]    one thread per low-res pixel, coalesced over px
+// Weights come from the forward's own index / weight arithmetic (upsample_axis).  Support bounds: i0 in {p-1, p} <=>
+// real = r*i in [p-1, p+1), and 1/r = s + (s-1)/(n_in-1) lies in [s, 2s): i in [(p-1)*s - 1, (p+1)*s + 2s]; exact
+// membership is decided per element.
+// G lanes (a power of two <= 32, about half the stride) share one output and combine with a fixed-order xor butterfly.
+template <int G>
+__global__ void __launch_bounds__(256) upsample_adjoint_h_kernel(int B, int H, int W, int w, float rx, const float* __restrict__ gfull,
+                                                                 float* __restrict__ T)
 {
-    const int lane = threadIdx.x & 31;
-    const long long wid = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    if (wid >= (long long)B * h * w) return;
-    const int px = (int)(wid % w), py = (int)((wid / w) % h), b = (int)(wid / ((long long)w * h));
-    // generous bounds of the support (rows whose i0 or i1 can equal py), exact membership is tested per element
-    const int sy = H / h, sx = W / w;
-    const int vlo = max(0, (py - 1) * sy - sy), vhi = min(H - 1, (py + 1) * sy + sy);
-    const int ulo = max(0, (px - 1) * sx - sx), uhi = min(W - 1, (px + 1) * sx + sx);
-    const int ncol = uhi - ulo + 1;
-    double acc = 0.0;
-    const float* g = gfull + (size_t)b * H * W;
-    for (int v = vlo; v <= vhi; v++) {
-        int y0, y1; float ly0, ly1;
-        upsample_axis(ry, v, h, y0, y1, ly0, ly1);
-        const float wy = (y0 == py ? ly0 : 0.f) + (y1 == py ? ly1 : 0.f);
-        if (wy == 0.f) continue;      // warp-uniform
-        for (int c = lane; c < ncol; c += 32) {
-            const int u = ulo + c;
+    const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long idx = gid / G;
+    const int sub = (int)(gid % G);
+    const bool live = idx < (long long)B * H * w;
+    float acc = 0.f;
+    if (live) {
+        const int px = (int)(idx % w);
+        const long long row = idx / w;                    // b * H + v
+        const int sx = W / w;
+        const int ulo = max(0, (px - 1) * sx - 1), uhi = min(W - 1, (px + 1) * sx + 2 * sx);
+        const float* g = gfull + (size_t)row * W;
+        for (int u = ulo + sub; u <= uhi; u += G) {
             int x0, x1; float lx0, lx1;
             upsample_axis(rx, u, w, x0, x1, lx0, lx1);
             const float wx = (x0 == px ? lx0 : 0.f) + (x1 == px ? lx1 : 0.f);
-            if (wx != 0.f) acc += (double)(wy * wx) * (double)__ldg(g + (size_t)v * W + u);
+            if (wx != 0.f) acc = fmaf(wx, __ldg(g + u), acc);
         }
     }
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-    if (lane == 0) glow[((size_t)b * h + py) * w + px] = (float)acc;
+    for (int o = G / 2; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (live && sub == 0) T[idx] = acc;
+}
+
+template <int G>
+__global__ void __launch_bounds__(256) upsample_adjoint_v_kernel(int B, int H, int h, int w, float ry, const float* __restrict__ T,
+                                                                 float* __restrict__ glow)
+{
+    const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long idx = gid / G;
+    const int sub = (int)(gid % G);
+    const bool live = idx < (long long)B * h * w;
+    double acc = 0.0;
+    if (live) {
+        const int px = (int)(idx % w), py = (int)((idx / w) % h), b = (int)(idx / ((long long)w * h));
+        const int sy = H / h;
+        const int vlo = max(0, (py - 1) * sy - 1), vhi = min(H - 1, (py + 1) * sy + 2 * sy);
+        const float* t = T + (size_t)b * H * w + px;
+        for (int v = vlo + sub; v <= vhi; v += G) {
+            int y0, y1; float ly0, ly1;
+            upsample_axis(ry, v, h, y0, y1, ly0, ly1);
+            const float wy = (y0 == py ? ly0 : 0.f) + (y1 == py ? ly1 : 0.f);
+            if (wy != 0.f) acc += (double)wy * (double)__ldg(t + (size_t)v * w);
+        }
+    }
+#pragma unroll
+    for (int o = G / 2; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (live && sub == 0) glow[idx] = (float)acc;
+}
+
+template <int G>
+static void launch_upsample_adjoint(int B, int H, int W, int h, int w, float ry, float rx, const float* gfull, float* T, float* glow, cudaStream_t st)
+{
+    const long long n1 = (long long)B * H * w * G, n2 = (long long)B * h * w * G;
+    upsample_adjoint_h_kernel<G><<<(unsigned)((n1 + 255) / 256), 256, 0, st>>>(B, H, W, w, rx, gfull, T);
+    upsample_adjoint_v_kernel<G><<<(unsigned)((n2 + 255) / 256), 256, 0, st>>>(B, H, h, w, ry, T, glow);
 }
 
 static int check_problem(const MgvsProblem* p)
@@ -744,6 +780,7 @@ int mgvs_backward(const MgvsProblem* p, const unsigned char* sel, const double* 
         // down into the caller's low-resolution grad_inv[i]
         char* gfull = (char*)p->stash + stash_texel_bytes(p->B, p->H, p->W, p->n) + stash_weight_bytes(p->B, p->H, p->W);
         const size_t gfull_stride = align256((size_t)p->B * p->H * p->W * sizeof(float));
+        float* adjT = (float*)(gfull + (size_t)p->n * gfull_stride);
         sp.lowres = lowres;
         for (int i = 0; i < p->n; i++) {
             sp.inv[i] = p->inv_depth[i];
@@ -778,9 +815,11 @@ int mgvs_backward(const MgvsProblem* p, const unsigned char* sel, const double* 
         kern<<<L.tiles, NT, BS_SMEM_BYTES, st>>>(sp, smaps);
         pose_reduce_kernel<<<p->B * S, 128, 0, st>>>(L.tiles_x * L.tiles_y, sp.pose_partials, p->poses, grad_poses);
         for (int i = 0; i < p->n && lowres; i++) {
-            const long long warps = (long long)p->B * sp.inv_h[i] * sp.inv_w[i];
-            upsample_adjoint_kernel<<<(unsigned)((warps * 32 + 255) / 256), 256, 0, st>>>(p->B, p->H, p->W, sp.inv_h[i], sp.inv_w[i], sp.inv_ry[i],
-                                                                                         sp.inv_rx[i], sp.grad_inv[i], grad_inv[i]);
+            const int stride = p->H / sp.inv_h[i];
+            #define MGVS_ADJ(G) launch_upsample_adjoint<G>(p->B, p->H, p->W, sp.inv_h[i], sp.inv_w[i], sp.inv_ry[i], sp.inv_rx[i], sp.grad_inv[i], adjT, grad_inv[i], st)
+            if (stride >= 64) MGVS_ADJ(32); else if (stride >= 32) MGVS_ADJ(16); else if (stride >= 16) MGVS_ADJ(8);
+            else if (stride >= 8) MGVS_ADJ(4); else if (stride >= 4) MGVS_ADJ(2); else MGVS_ADJ(1);
+            #undef MGVS_ADJ
         }
         return check_launch("mgvs_backward (stash)");
     }

@@ -225,7 +225,7 @@ class _ViewSynthesisLoss(torch.autograd.Function):
             stream = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
             _lib.check(L.mgvs_backward(ctypes.byref(prob), sel.data_ptr(), sums.data_ptr(), g.data_ptr(), arr,
                                        gp.data_ptr(), stream), "mgvs_backward")
-            launch_counter.n += BWD_LAUNCHES + (len(inv) if ctx.cfg.fuse_upsample else 0)   # + upsample_adjoint_kernel per scale
+            launch_counter.n += BWD_LAUNCHES + (2 * len(inv) if ctx.cfg.fuse_upsample else 0)   # + two upsample-adjoint kernels per scale
         ctx.stash = None
         return (None, gp, None, None, None, None, None) + tuple(grads)
 
