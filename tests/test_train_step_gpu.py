@@ -36,12 +36,13 @@ class TinyDepthNet(nn.Module):
         ])
         self.heads = nn.ModuleList([nn.Conv2d(c, 1, 3, 1, 1), nn.Conv2d(2 * c, 1, 3, 1, 1), nn.Conv2d(4 * c, 1, 3, 1, 1)])
 
-    def forward(self, x):
+    def forward(self, x, upsample=True):
         out, f = [], x
         for enc, head, stride in zip(self.enc, self.heads, (8, 16, 32)):
             f = enc(f)
             y = head(f).sigmoid() / 0.5                                                    # mg_net.py:823
-            out.append(F.interpolate(y, scale_factor=stride, mode="bilinear", align_corners=True))   # mg_net.py:803-806
+            # mg_net.py:803-806; with the fused loss (fuse_upsample=True) the low-resolution map is handed over as is
+            out.append(F.interpolate(y, scale_factor=stride, mode="bilinear", align_corners=True) if upsample else y)
         return out
 
 
@@ -55,10 +56,10 @@ class TinyPoseNet(nn.Module):
         return 0.01 * y.view(-1, 2, 6)                                                      # layers.py:166
 
 
-def _step(depth_net, pose_net, loss_fn, tgt):
+def _step(depth_net, pose_net, loss_fn, tgt, upsample=True):
     for p in list(depth_net.parameters()) + list(pose_net.parameters()):
         p.grad = None
-    pred = {"depth": depth_net(tgt["image_orig"]), "poses": pose_net(tgt["image_orig"], tgt["image_prev_orig"], tgt["image_next_orig"])}
+    pred = {"depth": depth_net(tgt["image_orig"], upsample), "poses": pose_net(tgt["image_orig"], tgt["image_prev_orig"], tgt["image_next_orig"])}
     out = loss_fn(pred, tgt)
     (out["loss_photometric"] + out["loss_smoothness"]).backward()
     return out
@@ -81,20 +82,22 @@ def test_training_step_eager_vs_fused(shape):
     torch.backends.cuda.matmul.allow_tf32 = False
 
     fused = MultiViewPhotometricLoss(photometric_reduce_op="min", padding_mode="zeros", **HP)
+    fused_up = MultiViewPhotometricLoss(photometric_reduce_op="min", padding_mode="zeros", fuse_upsample=True, **HP)
 
     def eager(pred, t):
         return reference_loss(pred, t, **HP)
 
     params = list(depth_net.parameters()) + list(pose_net.parameters())
     res = {}
-    for name, fn in (("eager", eager), ("fused", fused)):
+    for name, fn in (("eager", eager), ("fused", fused), ("fused_upsample", fused_up)):
+        up = name != "fused_upsample"
         for _ in range(3):
-            out = _step(depth_net, pose_net, fn, tgt)
+            out = _step(depth_net, pose_net, fn, tgt, up)
         torch.cuda.synchronize()
         t0 = time.perf_counter()
         K = 5
         for _ in range(K):
-            out = _step(depth_net, pose_net, fn, tgt)
+            out = _step(depth_net, pose_net, fn, tgt, up)
         torch.cuda.synchronize()
         res[name] = dict(ms=(time.perf_counter() - t0) / K * 1e3, lp=out["loss_photometric"].item(), ls=out["loss_smoothness"].item(),
                          grads=[p.grad.detach().clone() for p in params])
@@ -106,8 +109,14 @@ def test_training_step_eager_vs_fused(shape):
     den = sum(float(b.double().pow(2).sum()) for b in res["eager"]["grads"])
     rel = (num / den) ** 0.5
     assert rel <= 2e-2, rel
+    # the fused upsample is the same computation (bit-identical forward for outputs this large)
+    assert res["fused_upsample"]["lp"] == res["fused"]["lp"] and res["fused_upsample"]["ls"] == res["fused"]["ls"]
+    num = sum(float((a.double() - b.double()).pow(2).sum()) for a, b in zip(res["fused_upsample"]["grads"], res["fused"]["grads"]))
+    rel_up = (num / den) ** 0.5
+    assert rel_up <= 1e-4, rel_up
     line = {"workload": "training step, tiny depth+pose nets, B%d %dx%d, 3 scales" % (B, H, W), "step_ms_eager_loss": res["eager"]["ms"],
-            "step_ms_fused_loss": res["fused"]["ms"], "param_grad_l2rel": rel,
+            "step_ms_fused_loss": res["fused"]["ms"], "step_ms_fused_loss_and_upsample": res["fused_upsample"]["ms"],
+            "param_grad_l2rel": rel, "param_grad_l2rel_fused_upsample_vs_fused": rel_up,
             "loss_rel": abs(res["fused"]["lp"] - res["eager"]["lp"]) / abs(res["eager"]["lp"])}
     print("\nTRAIN_STEP " + json.dumps(line))
     out_dir = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out")
