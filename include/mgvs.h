@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define MGVS_ABI_VERSION 4
+#define MGVS_ABI_VERSION 5
 #define MGVS_MAX_SCALES 8   /* n: number of inverse-depth maps (reference: 3, mg_net.py:760-764) */
 #define MGVS_NUM_SOURCES 2  /* S: prev, next -- hard-coded in the reference (loss.py:116) */
 
@@ -150,6 +150,50 @@ int mgvs_reconstruct(int B, int H, int W, const float *depth, const float *camer
  * pose34 [B,3,4] = Tcw for frame "w", NULL for frame "c". */
 int mgvs_project(int B, int H, int W, const float *points, const float *camera, long long cam_batch_stride,
                  long long cam_row_stride, const float *pose34, float *coords, void *cuda_stream);
+
+
+/* ---- DGC depth rescaling at inference time -------------------------------------------------------
+ * Replaces get_depth_prediction(depth_logits, use_dgc_scaling, camera_matrix, real_camera_height, panoptic_seg,
+ * road_class_id, depth_filter_class_ids) (mgnet/postprocessing/depth_post_proc.py:11-71) together with its helpers
+ * _get_scale_recovery (:74-104), _get_surface_normal (:107-151), _get_ground_mask (:154-185) and
+ * Camera.reconstruct(frame="c") (mgnet/geometry/camera.py:107-136); exportable_post_proc.py:52-79 is the same
+ * arithmetic with the inverse camera matrix handed in (camera_is_inverse).  Results are bit-identical to the
+ * reference on CPU (points, normals, camera heights, ground mask, median, scale factor).  The reference handles one
+ * image per call; B > 1 runs B independent images (one median each). */
+#define MGVS_DGC_MAX_FILTER 16
+enum { MGVS_PANOPTIC_NONE = 0, MGVS_PANOPTIC_I64 = 1, MGVS_PANOPTIC_I32 = 2 };
+
+typedef struct MgvsDgcProblem {
+    int B, H, W;                    /* H, W >= 3 (the normals use a 3x3 neighbourhood) */
+    float *depth;                   /* depth_logits [B,1,H,W], rescaled IN PLACE like `depth_logits *= scale_factor`
+                                       (depth_post_proc.py:58) */
+    const float *camera;            /* camera_matrix; element (b,r,c) at camera[b*cam_batch_stride + r*cam_row_stride + c] */
+    long long cam_batch_stride, cam_row_stride;
+    int camera_is_inverse;          /* 0: K, the library forms Camera.Kinv (camera.py:72-81); 1: K^-1 given
+                                       (exportable_post_proc.py:66-68) */
+    const float *real_camera_height;/* device, element b at real_camera_height[b*height_stride] (stride 0 = shared) */
+    long long height_stride;
+    const void *panoptic;           /* panoptic_seg [B,H,W] int64 / int32, or NULL */
+    int panoptic_dtype;             /* MGVS_PANOPTIC_* */
+    int use_dgc;                    /* use_dgc_scaling; 0 = only the class filter runs (needs panoptic) */
+    long long road_class_id;        /* ground mask = panoptic == road_class_id; with panoptic == NULL the ground mask
+                                       comes from the surface normals (depth_post_proc.py:154-185) */
+    long long filter_ids[MGVS_DGC_MAX_FILTER]; /* depth_filter_class_ids: depth -> 0, points -> NaN where panoptic == id */
+    int n_filter;
+    float *points;                  /* cam_xyz_points [B,3,H,W] out (already scaled), or NULL */
+    float *scale;                   /* [B] out: scale_factor; NaN when the ground mask is empty or holds a NaN height
+                                       (what torch.median yields in the reference) */
+    long long *count;               /* [B] out or NULL: 0 iff the ground mask of image b is empty */
+    void *workspace;                /* >= mgvs_dgc_workspace_bytes(B,H,W), 256-byte aligned */
+    size_t workspace_bytes;
+} MgvsDgcProblem;
+
+size_t mgvs_dgc_workspace_bytes(int B, int H, int W);
+/* 5 stream operations (1 memset + 4 kernels), no host synchronisation, graph capturable. */
+int mgvs_dgc_rescale(const MgvsDgcProblem *p, void *cuda_stream);
+/* Diagnostics for the parity tests: per-pixel camera heights [B,H,W] (|P.N|, depth_post_proc.py:96) and the ground
+ * mask [B,H,W] uint8 that the median runs over.  Same inputs as mgvs_dgc_rescale; depth is not modified. */
+int mgvs_dgc_heights(const MgvsDgcProblem *p, float *heights, unsigned char *ground, void *cuda_stream);
 
 /* Self-test hook used by the GPU tests: out[i] = a[i] / b[i] with the library's in-kernel exact division. */
 int mgvs_test_div(const float *a, const float *b, float *out, long long count, void *cuda_stream);

@@ -15,7 +15,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _CSRC = os.path.join(_HERE, "csrc")
 LIB_PATH = os.environ.get("MGVS_LIB_PATH") or os.path.join(_HERE, "libmgvs.so")   # override: kernel-variant experiments only
 MAX_SCALES = 8
-ABI_VERSION = 4
+ABI_VERSION = 5
 IMAGE_F32, IMAGE_U8 = 0, 1
 NUM_SOURCES = 2
 
@@ -42,6 +42,33 @@ class MgvsProblem(ctypes.Structure):
         ("image_dtype", ctypes.c_int),
         ("stash", ctypes.c_void_p), ("stash_bytes", ctypes.c_size_t),
         ("inv_height", ctypes.c_int * MAX_SCALES), ("inv_width", ctypes.c_int * MAX_SCALES),
+    ]
+
+
+DGC_MAX_FILTER = 16
+PANOPTIC_NONE, PANOPTIC_I64, PANOPTIC_I32 = 0, 1, 2
+
+
+class MgvsDgcProblem(ctypes.Structure):
+    """include/mgvs.h: MgvsDgcProblem (DGC depth rescaling, reference depth_post_proc.py:11-185)."""
+    _fields_ = [
+        ("B", ctypes.c_int), ("H", ctypes.c_int), ("W", ctypes.c_int),
+        ("depth", ctypes.c_void_p),
+        ("camera", ctypes.c_void_p),
+        ("cam_batch_stride", ctypes.c_longlong), ("cam_row_stride", ctypes.c_longlong),
+        ("camera_is_inverse", ctypes.c_int),
+        ("real_camera_height", ctypes.c_void_p),
+        ("height_stride", ctypes.c_longlong),
+        ("panoptic", ctypes.c_void_p),
+        ("panoptic_dtype", ctypes.c_int),
+        ("use_dgc", ctypes.c_int),
+        ("road_class_id", ctypes.c_longlong),
+        ("filter_ids", ctypes.c_longlong * DGC_MAX_FILTER),
+        ("n_filter", ctypes.c_int),
+        ("points", ctypes.c_void_p),
+        ("scale", ctypes.c_void_p),
+        ("count", ctypes.c_void_p),
+        ("workspace", ctypes.c_void_p), ("workspace_bytes", ctypes.c_size_t),
     ]
 
 
@@ -121,6 +148,13 @@ def lib():
     L.mgvs_reconstruct.argtypes = [ci, ci, ci, vp, vp, ll, ll, vp, vp]
     L.mgvs_project.restype = ci
     L.mgvs_project.argtypes = [ci, ci, ci, vp, vp, ll, ll, vp, vp, vp]
+    DP = ctypes.POINTER(MgvsDgcProblem)
+    L.mgvs_dgc_workspace_bytes.restype = ctypes.c_size_t
+    L.mgvs_dgc_workspace_bytes.argtypes = [ci, ci, ci]
+    L.mgvs_dgc_rescale.restype = ci
+    L.mgvs_dgc_rescale.argtypes = [DP, vp]
+    L.mgvs_dgc_heights.restype = ci
+    L.mgvs_dgc_heights.argtypes = [DP, vp, vp, vp]
     L.mgvs_test_div.restype = ci
     L.mgvs_test_div.argtypes = [vp, vp, vp, ll, vp]
     if L.mgvs_abi_version() != ABI_VERSION:
@@ -132,6 +166,7 @@ def lib():
 EXPORTED_SYMBOLS = (
     "mgvs_abi_version", "mgvs_last_error", "mgvs_num_sums", "mgvs_workspace_bytes", "mgvs_workspace_bytes_ex", "mgvs_stash_bytes", "mgvs_stash_bytes_ex", "mgvs_forward", "mgvs_forward_losses",
     "mgvs_finalize", "mgvs_backward", "mgvs_view_synthesis", "mgvs_reconstruct", "mgvs_project", "mgvs_test_div",
+    "mgvs_dgc_workspace_bytes", "mgvs_dgc_rescale", "mgvs_dgc_heights",
 )
 
 

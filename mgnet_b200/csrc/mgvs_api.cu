@@ -2,6 +2,7 @@
 // extern "C" entry points declared in include/mgvs.h.  Built for sm_100a only.
 #include <cuda.h>
 #include <cuda_runtime.h>
+#include <algorithm>
 #include <math.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -10,6 +11,7 @@
 #include "../../include/mgvs.h"
 #include "mgvs_bwd.cuh"
 #include "mgvs_bwd_stash.cuh"
+#include "mgvs_dgc.cuh"
 #include "mgvs_fwd.cuh"
 
 namespace mgvs {
@@ -649,6 +651,61 @@ static int check_launch(const char* what)
     return MGVS_OK;
 }
 
+
+// ---- DGC depth rescaling (mgvs_dgc.cuh) -------------------------------------------------------------------------
+static size_t dgc_state_bytes(int B) { return align256((size_t)B * sizeof(dgc::State)); }
+
+static int dgc_check(const MgvsDgcProblem* p)
+{
+    if (!p) return fail(MGVS_EINVAL, "null problem");
+    if (p->B < 1 || p->H < 3 || p->W < 3) return fail(MGVS_EINVAL, "bad dims (need B>=1, H,W>=3)");
+    if ((long long)p->H * p->W >= (1ll << 31)) return fail(MGVS_EINVAL, "image plane too large for 32-bit counters");
+    if (!p->depth) return fail(MGVS_EINVAL, "null depth pointer");
+    if (p->panoptic_dtype != MGVS_PANOPTIC_NONE && p->panoptic_dtype != MGVS_PANOPTIC_I64 && p->panoptic_dtype != MGVS_PANOPTIC_I32)
+        return fail(MGVS_EINVAL, "panoptic_dtype must be MGVS_PANOPTIC_NONE / _I64 / _I32");
+    if ((p->panoptic != nullptr) != (p->panoptic_dtype != MGVS_PANOPTIC_NONE)) return fail(MGVS_EINVAL, "panoptic pointer and panoptic_dtype disagree");
+    if (p->n_filter < 0 || p->n_filter > MGVS_DGC_MAX_FILTER) return fail(MGVS_EINVAL, "n_filter must be 0..16");
+    if (p->use_dgc) {
+        if (!p->camera) return fail(MGVS_EINVAL, "camera_matrix is necessary for dgc rescaling!");          // depth_post_proc.py:44
+        if (!p->real_camera_height) return fail(MGVS_EINVAL, "real_camera_height is necessary for dgc rescaling!");  // :45
+        if (!p->scale) return fail(MGVS_EINVAL, "null scale output");
+        if (!p->workspace || ((uintptr_t)p->workspace & 255)) return fail(MGVS_EINVAL, "workspace null or not 256-byte aligned");
+        if (p->workspace_bytes < mgvs_dgc_workspace_bytes(p->B, p->H, p->W)) return fail(MGVS_EWORKSPACE, "workspace too small");
+    } else if (p->points) {
+        return fail(MGVS_EINVAL, "points are only produced with use_dgc (the reference returns None, depth_post_proc.py:42)");
+    }
+    return MGVS_OK;
+}
+
+template <typename PanT>
+static void dgc_launch_heights(const MgvsDgcProblem* p, unsigned* keys, dgc::State* states, float* dbg_h, unsigned char* dbg_g, cudaStream_t st)
+{
+    dim3 grid((p->W + dgc::TW - 1) / dgc::TW, (p->H + dgc::TH - 1) / dgc::TH, p->B);
+    if (p->panoptic)
+        dgc::dgc_heights_kernel<PanT, false><<<grid, dgc::NT, 0, st>>>(p->H, p->W, p->depth, p->camera, p->cam_batch_stride, p->cam_row_stride,
+                                                                      p->camera_is_inverse, p->panoptic, p->road_class_id, keys, states, dbg_h, dbg_g);
+    else
+        dgc::dgc_heights_kernel<PanT, true><<<grid, dgc::NT, 0, st>>>(p->H, p->W, p->depth, p->camera, p->cam_batch_stride, p->cam_row_stride,
+                                                                     p->camera_is_inverse, nullptr, 0, keys, states, dbg_h, dbg_g);
+}
+
+template <typename PanT>
+static void dgc_launch_apply(const MgvsDgcProblem* p, const dgc::State* states, cudaStream_t st)
+{
+    const size_t HW = (size_t)p->H * p->W;
+    dgc::FilterIds ids;
+    ids.n = p->panoptic ? p->n_filter : 0;
+    for (int k = 0; k < dgc::MAX_FILTER; k++) ids.id[k] = k < ids.n ? p->filter_ids[k] : 0;
+    const bool vec = (p->W % 4 == 0) && (((uintptr_t)p->depth & 15) == 0) && (!p->points || ((uintptr_t)p->points & 15) == 0);
+    const size_t per_block = (size_t)dgc::NT * (vec ? 4 : 1);
+    const unsigned gx = (unsigned)std::min<size_t>((HW + per_block - 1) / per_block, (size_t)148 * 8);
+    dim3 grid(gx, p->B);
+    auto kern = vec ? dgc::dgc_apply_kernel<PanT, true> : dgc::dgc_apply_kernel<PanT, false>;
+    kern<<<grid, dgc::NT, 0, st>>>(p->H, p->W, p->depth, p->camera, p->cam_batch_stride, p->cam_row_stride, p->camera_is_inverse,
+                                   p->real_camera_height, p->height_stride, p->panoptic, ids, p->use_dgc, p->points, p->scale,
+                                   p->count, states);
+}
+
 }  // namespace mgvs
 
 using namespace mgvs;
@@ -886,6 +943,47 @@ int mgvs_project(int B, int H, int W, const float* points, const float* camera, 
     project_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)cuda_stream>>>(
         B, H, W, points, camera, cam_batch_stride, cam_row_stride, pose34, coords);
     return check_launch("mgvs_project");
+}
+
+size_t mgvs_dgc_workspace_bytes(int B, int H, int W)
+{
+    if (B < 1 || H < 1 || W < 1) return 0;
+    return dgc_state_bytes(B) + align256((size_t)B * H * W * sizeof(unsigned));
+}
+
+static int dgc_run(const MgvsDgcProblem* p, float* dbg_h, unsigned char* dbg_g, bool apply, cudaStream_t st)
+{
+    dgc::State* states = (dgc::State*)p->workspace;
+    unsigned* keys = (unsigned*)((char*)p->workspace + dgc_state_bytes(p->B));
+    if (p->use_dgc) {
+        cudaMemsetAsync(states, 0, (size_t)p->B * sizeof(dgc::State), st);
+        if (p->panoptic_dtype == MGVS_PANOPTIC_I32) dgc_launch_heights<int>(p, keys, states, dbg_h, dbg_g, st);
+        else dgc_launch_heights<long long>(p, keys, states, dbg_h, dbg_g, st);
+        if (!apply) return check_launch("mgvs_dgc_heights");
+        const size_t HW = (size_t)p->H * p->W;
+        dim3 rgrid((unsigned)std::min<size_t>((HW + dgc::NT - 1) / dgc::NT, (size_t)148 * 4), p->B);
+        dgc::dgc_refine_kernel<2><<<rgrid, dgc::NT, 0, st>>>(HW, keys, states);
+        dgc::dgc_refine_kernel<3><<<rgrid, dgc::NT, 0, st>>>(HW, keys, states);
+    }
+    if (p->panoptic_dtype == MGVS_PANOPTIC_I32) dgc_launch_apply<int>(p, states, st);
+    else dgc_launch_apply<long long>(p, states, st);
+    return check_launch("mgvs_dgc_rescale");
+}
+
+int mgvs_dgc_rescale(const MgvsDgcProblem* p, void* cuda_stream)
+{
+    int rc = dgc_check(p);
+    if (rc) return rc;
+    if (!p->use_dgc && (!p->panoptic || p->n_filter == 0)) return MGVS_OK;   // nothing to do (depth_post_proc.py:59-69)
+    return dgc_run(p, nullptr, nullptr, true, (cudaStream_t)cuda_stream);
+}
+
+int mgvs_dgc_heights(const MgvsDgcProblem* p, float* heights, unsigned char* ground, void* cuda_stream)
+{
+    int rc = dgc_check(p);
+    if (rc) return rc;
+    if (!p->use_dgc) return fail(MGVS_EINVAL, "mgvs_dgc_heights needs use_dgc");
+    return dgc_run(p, heights, ground, false, (cudaStream_t)cuda_stream);
 }
 
 int mgvs_test_div(const float* a, const float* b, float* out, long long count, void* cuda_stream)

@@ -144,3 +144,45 @@ def bytes_per_pixel(n: int, S: int = 2, mask: bool = True, fwd_only: bool = Fals
     m = 1 if mask else 0
     fwd = 12 + 12 * S + 4 * n + m
     return fwd if fwd_only else 2 * fwd + 4 * n
+
+
+def make_dgc_inputs(H: int, W: int, seed: int = 0, scale_true: float = 7.5, cam_height: float = 1.65,
+                    with_panoptic: bool = True, road_class_id: int = 0, label_divisor: int = 1000):
+    """Synthetic inference-time scene for the DGC depth rescaling (reference depth_post_proc.py:11-104).
+
+    A pinhole camera ``cam_height`` metres above a slightly bumpy ground plane (y points down), a far "sky" above the
+    horizon and two box-like obstacles; the network's depth is the metric depth divided by ``scale_true`` (what an
+    unscaled self-supervised depth head produces), so the recovered scale factor should be close to ``scale_true``.
+    Returns a dict of CPU tensors: depth [1,1,H,W], camera_matrix [1,3,3], real_camera_height [1], and (optionally)
+    panoptic_seg [H,W] int64 in the reference's ``trainId * label_divisor`` convention (road / obstacle / sky).
+    """
+    g = _gen(seed * 1000 + 70)
+    K = kitti_like_K(1, H, W)[:, :3, :3].contiguous()
+    fx, fy, cx, cy = K[0, 0, 0], K[0, 1, 1], K[0, 0, 2], K[0, 1, 2]
+    v = torch.arange(H, dtype=torch.float32).view(H, 1).expand(H, W)
+    u = torch.arange(W, dtype=torch.float32).view(1, W).expand(H, W)
+    ry = (v - cy) / fy
+    bump = 1.0 + 0.02 * (_smooth_field((1, 1, H, W), g, cell=8)[0, 0] - 0.5)
+    z_ground = cam_height * bump / ry.clamp(min=1e-3)
+    far = 60.0 + 20.0 * _smooth_field((1, 1, H, W), g, cell=16)[0, 0]
+    z = torch.where(ry > 0.02, torch.minimum(z_ground, far), far)
+    pan = torch.full((H, W), 10 * label_divisor, dtype=torch.int64)          # sky / far
+    pan[(ry > 0.02) & (z_ground < far)] = road_class_id
+    # two fronto-parallel obstacles standing on the ground
+    for k, (u0, u1, zobj) in enumerate(((0.15, 0.3, 9.0), (0.6, 0.8, 15.0))):
+        cols = (u >= u0 * W) & (u < u1 * W)
+        top = cy - 1.2 * fy / zobj
+        rows = (v >= top) & (z > zobj)
+        sel = cols & rows
+        z = torch.where(sel, torch.full_like(z, zobj), z)
+        pan[sel] = (13 + k) * label_divisor + 1 + k
+    z = z * (1.0 + 0.004 * (torch.rand(H, W, generator=g) - 0.5))
+    depth = (z / scale_true).view(1, 1, H, W).contiguous()
+    out = {
+        "depth": depth,
+        "camera_matrix": K,
+        "real_camera_height": torch.tensor([cam_height], dtype=torch.float32),
+    }
+    if with_panoptic:
+        out["panoptic_seg"] = pan.contiguous()
+    return out

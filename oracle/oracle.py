@@ -13,25 +13,31 @@ import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB_PATH = os.path.join(_HERE, "libmgvs_oracle.so")
+_DGC_LIB_PATH = os.path.join(_HERE, "libdgc_oracle.so")
 MAX_SCALES = 8
 S = 2
 
 
-def build(force: bool = False) -> str:
-    """Compiles the C restatement in place (gcc, OpenMP if available)."""
-    src = os.path.join(_HERE, "mgvs_oracle.c")
-    if (not force) and os.path.isfile(_LIB_PATH) and os.path.getmtime(_LIB_PATH) >= os.path.getmtime(src):
-        return _LIB_PATH
-    base = ["-O2", "-mfma", "-ffp-contract=off", "-fPIC", "-std=gnu11", "-shared", "-o", _LIB_PATH, src, "-lm"]
+def _compile(src_name: str, lib_path: str, force: bool) -> str:
+    src = os.path.join(_HERE, src_name)
+    if (not force) and os.path.isfile(lib_path) and os.path.getmtime(lib_path) >= os.path.getmtime(src):
+        return lib_path
+    base = ["-O2", "-mfma", "-ffp-contract=off", "-fPIC", "-std=gnu11", "-shared", "-o", lib_path, src, "-lm"]
     last = None
     for cc in ("/usr/bin/gcc", "gcc", "cc"):
         for omp in (["-fopenmp"], []):
             try:
                 subprocess.run([cc] + omp + base, check=True, capture_output=True, text=True)
-                return _LIB_PATH
+                return lib_path
             except (subprocess.CalledProcessError, FileNotFoundError) as e:  # try next
                 last = e
     raise RuntimeError("could not build the oracle: %s" % (getattr(last, "stderr", last),))
+
+
+def build(force: bool = False) -> str:
+    """Compiles the C restatements in place (gcc, OpenMP if available): the loss oracle and the DGC oracle."""
+    _compile("dgc_oracle.c", _DGC_LIB_PATH, force)
+    return _compile("mgvs_oracle.c", _LIB_PATH, force)
 
 
 class _OrcIn(ctypes.Structure):
@@ -171,3 +177,52 @@ class Oracle:
         if rc != 0:
             raise RuntimeError("orc_backward failed: %d" % rc)
         return {"grad_depth": grads, "grad_poses": gp, "grad_Rt": gRt}
+
+
+# ---- DGC depth rescaling (oracle/dgc_oracle.c; reference depth_post_proc.py:11-185) ---------------------------
+_dgc = None
+
+
+def dgc_lib():
+    global _dgc
+    if _dgc is None:
+        build()
+        _dgc = ctypes.CDLL(_DGC_LIB_PATH)
+        vp = ctypes.c_void_p
+        _dgc.orc_dgc.restype = ctypes.c_int
+        _dgc.orc_dgc.argtypes = [ctypes.c_int, ctypes.c_int, vp, vp, ctypes.c_long, ctypes.c_int, ctypes.c_float, vp,
+                                 ctypes.c_longlong, vp, ctypes.c_int, vp, vp, vp, vp, vp, vp, vp]
+    return _dgc
+
+
+def dgc_depth_prediction(depth, camera_matrix, real_camera_height, panoptic_seg=None, road_class_id=-1,
+                         depth_filter_class_ids=None, camera_is_inverse=False):
+    """CPU oracle of ``get_depth_prediction(..., use_dgc_scaling=True)`` for one image.
+
+    depth [H,W] (or [1,1,H,W]), camera_matrix [3,3] (or [1,3,3]).  Returns a dict with depth [H,W], points [3,H,W],
+    normals [3,H,W], heights [H,W], ground [H,W] uint8, scale (np.float32), count, empty (bool: torch.median would raise).
+    """
+    d = _np(depth)
+    H, W = d.shape[-2:]
+    d = d.reshape(H, W)
+    cam = _np(camera_matrix).reshape(-1)[-9:].reshape(3, 3) if _np(camera_matrix).size == 9 else _np(camera_matrix)[..., :3, :3].reshape(3, 3).copy()
+    cam = np.ascontiguousarray(cam, np.float32)
+    pan = None if panoptic_seg is None else _np(panoptic_seg, np.int64).reshape(H, W)
+    ids = np.asarray(list(depth_filter_class_ids or []), np.int64)
+    out = {
+        "depth": np.zeros((H, W), np.float32), "points": np.zeros((3, H, W), np.float32),
+        "normals": np.zeros((3, H, W), np.float32), "heights": np.zeros((H, W), np.float32),
+        "ground": np.zeros((H, W), np.uint8),
+    }
+    scale = ctypes.c_float(0.0)
+    count = ctypes.c_longlong(0)
+    rh = float(_np(real_camera_height).reshape(-1)[0])
+    rc = dgc_lib().orc_dgc(H, W, _ptr(d), _ptr(cam), 3, int(bool(camera_is_inverse)), rh,
+                           _ptr(pan) if pan is not None else None, int(road_class_id),
+                           _ptr(ids) if ids.size else None, int(ids.size), _ptr(out["depth"]), _ptr(out["points"]),
+                           _ptr(out["normals"]), _ptr(out["heights"]), _ptr(out["ground"]), ctypes.byref(scale),
+                           ctypes.byref(count))
+    out["scale"] = np.float32(scale.value)
+    out["count"] = int(count.value)
+    out["empty"] = rc == 1
+    return out

@@ -147,3 +147,53 @@ def reference_loss(predictions, targets, ssim_loss_weight=0.85, photometric_loss
     if return_selection:
         out["selection"] = torch.stack([s[:, 0].to(torch.uint8) for s in sel], 0)
     return out
+
+
+# ---- DGC depth rescaling (reference mgnet/postprocessing/depth_post_proc.py:11-185), same ATen operator sequence ------
+def _dgc_surface_normal(P):
+    """_get_surface_normal (depth_post_proc.py:107-151), nei = 1."""
+    ctr = P[:, :, 1:-1, 1:-1]
+    def nb(dy, dx):
+        H, W = P.shape[-2:]
+        return P[:, :, 1 + dy:H - 1 + dy, 1 + dx:W - 1 + dx] - ctr
+    pairs = ((nb(0, -1), nb(-1, 0)), (nb(0, 1), nb(1, 0)), (nb(-1, -1), nb(1, -1)), (nb(-1, 1), nb(1, 1)))
+    ns = [F.normalize(torch.cross(a, b, dim=1), dim=1).unsqueeze(0) for a, b in pairs]
+    n = F.normalize(torch.cat(ns, dim=0).mean(0), dim=1)
+    return F.pad(n, (1, 1, 1, 1), "replicate")
+
+
+def reference_dgc(depth_logits, camera_matrix, real_camera_height, panoptic_seg=None, road_class_id=-1,
+                  depth_filter_class_ids=None):
+    """get_depth_prediction(..., use_dgc_scaling=True) as flat ATen calls on whatever device the inputs live on.
+    depth_logits [1,1,H,W] is modified in place like the reference does.  Returns (depth [H,W], points [3,H,W], scale)."""
+    import math
+    B, _, H, W = depth_logits.shape
+    K = camera_matrix.reshape(-1, 3, 3).to(depth_logits.device).float()
+    Kinv = K.clone()
+    fx, fy, cx, cy = K[:, 0, 0], K[:, 1, 1], K[:, 0, 2], K[:, 1, 2]
+    Kinv[:, 0, 0] = 1.0 / fx
+    Kinv[:, 1, 1] = 1.0 / fy
+    Kinv[:, 0, 2] = -1.0 * cx / fx
+    Kinv[:, 1, 2] = -1.0 * cy / fy
+    grid = _pixel_grid(B, H, W, depth_logits.dtype, depth_logits.device)
+    P = Kinv.bmm(grid).view(B, 3, H, W) * depth_logits
+    N = _dgc_surface_normal(P)
+    if panoptic_seg is not None:
+        ground = panoptic_seg == road_class_id
+    else:
+        thr = math.cos(math.radians(5))
+        vertical = torch.cat((torch.zeros_like(depth_logits), torch.ones_like(depth_logits), torch.zeros_like(depth_logits)), 1)
+        cs = torch.nn.CosineSimilarity(dim=1, eps=1e-6)(N, vertical).unsqueeze(1)
+        ground = ((cs > thr) | (cs < -thr)).masked_fill(P[:, 1].unsqueeze(1) <= 0, False)
+    heights = (P * N).sum(1).abs().unsqueeze(1)
+    med = torch.median(torch.masked_select(heights, ground)).unsqueeze(0)
+    scale = torch.reciprocal(med).mul_(real_camera_height.to(depth_logits.device))
+    depth_logits *= scale
+    P *= scale
+    P = P.squeeze(0)
+    out = depth_logits.squeeze(0).squeeze(0)
+    if panoptic_seg is not None:
+        for cid in (depth_filter_class_ids or []):
+            out[panoptic_seg == cid] = 0
+            P[:, panoptic_seg == cid] = float("nan")
+    return out, P, scale

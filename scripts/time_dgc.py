@@ -1,0 +1,104 @@
+"""SURVEY 8f-3 measurement: DGC depth rescaling of one image -- the fused sm_100a path (mgnet_b200.postprocessing) against
+(a) the reference's ATen operator sequence on the same GPU (oracle/torch_port.reference_dgc) and (b) the C oracle on the
+host cores.  Also times each kernel through the C ABI with CUDA events and reports the apply kernel against the HBM
+roofline.  Usage: python scripts/time_dgc.py [kitti city]"""
+import ctypes, json, os, sys, time
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import torch
+from mgnet_b200 import _lib
+from mgnet_b200.postprocessing import dgc_rescale, _problem, _prepare
+from mgnet_b200.synthetic import make_dgc_inputs
+from oracle.torch_port import reference_dgc
+from oracle.oracle import dgc_depth_prediction
+
+SIZES = {"kitti": (192, 640), "city": (1024, 2048)}
+dev = torch.device("cuda:0")
+peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else {}
+PEAK = float(peaks.get("hbm_gbs", 6552.0))
+out = {"hbm_peak_gbs": PEAK}
+
+
+def timed(fn, reps=50, warm=5):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / reps
+
+
+for name in (sys.argv[1:] or ["kitti", "city"]):
+    H, W = SIZES[name]
+    d = make_dgc_inputs(H, W, seed=3, scale_true=6.0)
+    src = d["depth"].to(dev)
+    # rotate over several copies so the 126 MB L2 does not hold the working set between iterations
+    NB = 12 if name == "city" else 64
+    bufs = [src.clone() for _ in range(NB)]
+    cam, hgt, pan = d["camera_matrix"].to(dev), d["real_camera_height"].to(dev), d["panoptic_seg"].to(dev)
+    pans = [pan.clone() for _ in range(NB)]
+    res = {}
+    for variant, use_pan in (("panoptic", True), ("auto_mask", False)):
+        k = [0]
+        def fused():
+            i = k[0] % NB; k[0] += 1
+            bufs[i].copy_(src)
+            return dgc_rescale(bufs[i], cam, hgt, pans[i] if use_pan else None, 0 if use_pan else -1, [10000] if use_pan else [])
+        def copy_only():
+            i = k[0] % NB; k[0] += 1
+            bufs[i].copy_(src)
+        def eager():
+            i = k[0] % NB; k[0] += 1
+            bufs[i].copy_(src)
+            return reference_dgc(bufs[i], cam, hgt, pans[i] if use_pan else None, 0 if use_pan else -1, [10000] if use_pan else [])
+        t_copy = timed(copy_only)
+        t_fused = timed(fused) - t_copy
+        t_eager = timed(eager, reps=10, warm=2) - t_copy
+        a = fused(); b = eager()
+        torch.cuda.synchronize()
+        same = bool(torch.equal(a[1], b[2]))
+        res[variant] = {"fused_ms": t_fused, "eager_torch_gpu_ms": t_eager, "speedup": t_eager / t_fused, "scale_equal_to_eager_cuda": same,
+                        "scale": float(a[1][0])}
+    # per-kernel timing through the C ABI (panoptic variant): heights-only entry point vs the full call
+    L = _lib.lib()
+    work = src.clone()
+    dl, camp, hp, panp = _prepare(work, cam, hgt, pan, True)
+    points = torch.empty((1, 3, H, W), device=dev); scale = torch.empty(1, device=dev); count = torch.empty(1, dtype=torch.int64, device=dev)
+    ws = torch.empty(int(L.mgvs_dgc_workspace_bytes(1, H, W)), dtype=torch.uint8, device=dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    prob = _problem(dl, camp, hp, panp, 0, [10000], True, False, points, scale, count, ws)
+    stream = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+    hts = torch.empty((1, H, W), device=dev); gr = torch.empty((1, H, W), dtype=torch.uint8, device=dev)
+    def t_call(fn, reps=20):
+        tot = 0.0
+        for _ in range(reps + 3):
+            work.copy_(src); flush.zero_()          # L2 flush between timed calls
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); fn(); e1.record(); torch.cuda.synchronize()
+            if _ >= 3:
+                tot += e0.elapsed_time(e1)
+        return tot / reps
+    t_full = t_call(lambda: L.mgvs_dgc_rescale(ctypes.byref(prob), stream))
+    t_heights = t_call(lambda: L.mgvs_dgc_heights(ctypes.byref(prob), None, None, stream))
+    px = H * W
+    alg = px * (4 + 8 + 4 + 12)          # read depth + int64 panoptic, write depth + 3 point planes (the minimum any implementation moves)
+    res["c_abi_cold_l2"] = {"rescale_ms": t_full, "heights_stage_ms": t_heights, "algorithmic_bytes": alg,
+                            "achieved_gbs": alg / (t_full * 1e-3) / 1e9, "frac_of_hbm_peak": alg / (t_full * 1e-3) / 1e9 / PEAK}
+    # CPU oracle on the host cores
+    t0 = time.perf_counter()
+    o = dgc_depth_prediction(d["depth"], d["camera_matrix"], d["real_camera_height"], d["panoptic_seg"], 0, [10000])
+    res["cpu_oracle_ms"] = (time.perf_counter() - t0) * 1e3
+    res["cpu_threads"] = os.cpu_count()
+    # the reference's own operator sequence on the host cores
+    dd = d["depth"].clone()
+    t0 = time.perf_counter()
+    reference_dgc(dd, d["camera_matrix"], d["real_camera_height"], d["panoptic_seg"], 0, [10000])
+    res["cpu_torch_port_ms"] = (time.perf_counter() - t0) * 1e3
+    out[name] = res
+    print(name, json.dumps(res))
+os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+json.dump(out, open(os.path.join(ROOT, "gpurun_out", "dgc_timing.json"), "w"), indent=1)

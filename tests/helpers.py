@@ -18,7 +18,7 @@ GRAD_RTOL = 1e-4
 def golden_names():
     """Full-resolution fixtures (the reference's contract).  "fused_*" fixtures hold low-resolution maps."""
     names = sorted(os.path.splitext(os.path.basename(p))[0] for p in glob.glob(os.path.join(GOLDEN, "*.npz")))
-    return [n for n in names if not n.startswith("fused_")]
+    return [n for n in names if not n.startswith(("fused_", "dgc_"))]
 
 
 def load_golden(name):

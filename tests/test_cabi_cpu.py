@@ -29,7 +29,7 @@ def test_header_symbols_exported():
 def test_host_side_queries():
     from mgnet_b200 import _lib
     L = _lib.lib()
-    assert L.mgvs_abi_version() == 4
+    assert L.mgvs_abi_version() == 5
     assert L.mgvs_num_sums(3) == 12
     ws = L.mgvs_workspace_bytes(16, 192, 640, 3)
     assert ws > 0 and ws % 256 == 0
@@ -46,11 +46,12 @@ def test_struct_layout_matches_header():
     from mgnet_b200 import _lib
     with tempfile.TemporaryDirectory() as d:
         src = os.path.join(d, "p.c")
-        open(src, "w").write('#include <stdio.h>\n#include "mgvs.h"\nint main(){printf("%zu\\n", sizeof(MgvsProblem));return 0;}\n')
+        open(src, "w").write('#include <stdio.h>\n#include "mgvs.h"\nint main(){printf("%zu %zu\\n", sizeof(MgvsProblem), sizeof(MgvsDgcProblem));return 0;}\n')
         exe = os.path.join(d, "p")
         subprocess.run(["/usr/bin/gcc", "-I", os.path.join(ROOT, "include"), "-o", exe, src], check=True)
-        size = int(subprocess.run([exe], capture_output=True, text=True, check=True).stdout)
+        size, dgc_size = map(int, subprocess.run([exe], capture_output=True, text=True, check=True).stdout.split())
     assert ctypes.sizeof(_lib.MgvsProblem) == size
+    assert ctypes.sizeof(_lib.MgvsDgcProblem) == dgc_size
 
 
 def test_module_rejects_unsupported_configs_loudly():
