@@ -195,6 +195,19 @@ int mgvs_dgc_rescale(const MgvsDgcProblem *p, void *cuda_stream);
  * mask [B,H,W] uint8 that the median runs over.  Same inputs as mgvs_dgc_rescale; depth is not modified. */
 int mgvs_dgc_heights(const MgvsDgcProblem *p, float *heights, unsigned char *ground, void *cuda_stream);
 
+/* ---- Homoscedastic uncertainty weighting of the task losses ---------------------------------------
+ * Replaces the epilogue of MGNet.forward (mgnet/modeling/mg_net.py:360-372):
+ *     losses[key] = tau * exp(-log_vars[idx]) * value + 0.5 * log_vars[idx]      tau = 1.0 for "loss_sem_seg" else 0.5
+ * and its two `.item()` host synchronisations per loss for the event storage (key + "_raw", key + "_uncertainty"):
+ * the logging copies are written to device memory instead.  k <= 16 losses; tau_host is a HOST array. */
+#define MGVS_MAX_LOSSES 16
+/*   raw [k], log_vars [k] in;  weighted [k] out;  log_out [2k] out or NULL: raw values, then exp(log_vars) */
+int mgvs_uncertainty_forward(int k, const float *raw, const float *log_vars, const float *tau_host, float *weighted,
+                             float *log_out, void *cuda_stream);
+/*   g_weighted [k] in;  g_raw [k] = g * tau * exp(-s);  g_log_vars [k] = g * (0.5 - tau * exp(-s) * raw) */
+int mgvs_uncertainty_backward(int k, const float *raw, const float *log_vars, const float *tau_host,
+                              const float *g_weighted, float *g_raw, float *g_log_vars, void *cuda_stream);
+
 /* Self-test hook used by the GPU tests: out[i] = a[i] / b[i] with the library's in-kernel exact division. */
 int mgvs_test_div(const float *a, const float *b, float *out, long long count, void *cuda_stream);
 

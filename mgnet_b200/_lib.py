@@ -46,6 +46,7 @@ class MgvsProblem(ctypes.Structure):
 
 
 DGC_MAX_FILTER = 16
+MAX_LOSSES = 16
 PANOPTIC_NONE, PANOPTIC_I64, PANOPTIC_I32 = 0, 1, 2
 
 
@@ -155,6 +156,10 @@ def lib():
     L.mgvs_dgc_rescale.argtypes = [DP, vp]
     L.mgvs_dgc_heights.restype = ci
     L.mgvs_dgc_heights.argtypes = [DP, vp, vp, vp]
+    L.mgvs_uncertainty_forward.restype = ci
+    L.mgvs_uncertainty_forward.argtypes = [ci, vp, vp, ctypes.POINTER(ctypes.c_float), vp, vp, vp]
+    L.mgvs_uncertainty_backward.restype = ci
+    L.mgvs_uncertainty_backward.argtypes = [ci, vp, vp, ctypes.POINTER(ctypes.c_float), vp, vp, vp, vp]
     L.mgvs_test_div.restype = ci
     L.mgvs_test_div.argtypes = [vp, vp, vp, ll, vp]
     if L.mgvs_abi_version() != ABI_VERSION:
@@ -167,6 +172,7 @@ EXPORTED_SYMBOLS = (
     "mgvs_abi_version", "mgvs_last_error", "mgvs_num_sums", "mgvs_workspace_bytes", "mgvs_workspace_bytes_ex", "mgvs_stash_bytes", "mgvs_stash_bytes_ex", "mgvs_forward", "mgvs_forward_losses",
     "mgvs_finalize", "mgvs_backward", "mgvs_view_synthesis", "mgvs_reconstruct", "mgvs_project", "mgvs_test_div",
     "mgvs_dgc_workspace_bytes", "mgvs_dgc_rescale", "mgvs_dgc_heights",
+    "mgvs_uncertainty_forward", "mgvs_uncertainty_backward",
 )
 
 

@@ -652,6 +652,31 @@ static int check_launch(const char* what)
 }
 
 
+// ---- uncertainty weighting epilogue (mg_net.py:360-372) --------------------------------------------------------
+struct TauArr { float v[MGVS_MAX_LOSSES]; };
+__global__ void uncertainty_fwd_kernel(int k, const float* __restrict__ raw, const float* __restrict__ log_vars, TauArr tau,
+                                       float* __restrict__ weighted, float* __restrict__ log_out)
+{
+    const int i = threadIdx.x;
+    if (i >= k) return;
+    const float s = log_vars[i], v = raw[i];
+    // tau * torch.exp(-s) * value + 0.5 * s, evaluated left to right with separate roundings like the eager expression
+    weighted[i] = __fadd_rn(__fmul_rn(__fmul_rn(tau.v[i], expf(-s)), v), __fmul_rn(0.5f, s));
+    if (log_out) {
+        log_out[i] = v;
+        log_out[k + i] = (float)exp((double)s);   // math.exp(log_var.item()) is a double evaluation
+    }
+}
+__global__ void uncertainty_bwd_kernel(int k, const float* __restrict__ raw, const float* __restrict__ log_vars, TauArr tau,
+                                       const float* __restrict__ g, float* __restrict__ g_raw, float* __restrict__ g_s)
+{
+    const int i = threadIdx.x;
+    if (i >= k) return;
+    const float s = log_vars[i], v = raw[i], w = __fmul_rn(tau.v[i], expf(-s));
+    g_raw[i] = __fmul_rn(g[i], w);
+    g_s[i] = __fmul_rn(g[i], __fsub_rn(0.5f, __fmul_rn(w, v)));
+}
+
 // ---- DGC depth rescaling (mgvs_dgc.cuh) -------------------------------------------------------------------------
 static size_t dgc_state_bytes(int B) { return align256((size_t)B * sizeof(dgc::State)); }
 
@@ -984,6 +1009,35 @@ int mgvs_dgc_heights(const MgvsDgcProblem* p, float* heights, unsigned char* gro
     if (rc) return rc;
     if (!p->use_dgc) return fail(MGVS_EINVAL, "mgvs_dgc_heights needs use_dgc");
     return dgc_run(p, heights, ground, false, (cudaStream_t)cuda_stream);
+}
+
+static int uncertainty_args(int k, const void* a, const void* b, const void* c, const float* tau_host, TauArr* t)
+{
+    if (k < 1 || k > MGVS_MAX_LOSSES) return fail(MGVS_EINVAL, "k must be 1..16");
+    if (!a || !b || !c || !tau_host) return fail(MGVS_EINVAL, "null argument");
+    for (int i = 0; i < MGVS_MAX_LOSSES; i++) t->v[i] = i < k ? tau_host[i] : 0.f;
+    return MGVS_OK;
+}
+
+int mgvs_uncertainty_forward(int k, const float* raw, const float* log_vars, const float* tau_host, float* weighted,
+                             float* log_out, void* cuda_stream)
+{
+    TauArr t;
+    int rc = uncertainty_args(k, raw, log_vars, weighted, tau_host, &t);
+    if (rc) return rc;
+    uncertainty_fwd_kernel<<<1, 32, 0, (cudaStream_t)cuda_stream>>>(k, raw, log_vars, t, weighted, log_out);
+    return check_launch("mgvs_uncertainty_forward");
+}
+
+int mgvs_uncertainty_backward(int k, const float* raw, const float* log_vars, const float* tau_host, const float* g_weighted,
+                              float* g_raw, float* g_log_vars, void* cuda_stream)
+{
+    TauArr t;
+    int rc = uncertainty_args(k, raw, log_vars, g_weighted, tau_host, &t);
+    if (rc) return rc;
+    if (!g_raw || !g_log_vars) return fail(MGVS_EINVAL, "null argument");
+    uncertainty_bwd_kernel<<<1, 32, 0, (cudaStream_t)cuda_stream>>>(k, raw, log_vars, t, g_weighted, g_raw, g_log_vars);
+    return check_launch("mgvs_uncertainty_backward");
 }
 
 int mgvs_test_div(const float* a, const float* b, float* out, long long count, void* cuda_stream)

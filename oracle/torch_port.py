@@ -197,3 +197,18 @@ def reference_dgc(depth_logits, camera_matrix, real_camera_height, panoptic_seg=
             out[panoptic_seg == cid] = 0
             P[:, panoptic_seg == cid] = float("nan")
     return out, P, scale
+
+
+def reference_uncertainty(losses, log_vars):
+    """The uncertainty epilogue of MGNet.forward (mg_net.py:360-372) as the same eager expression, minus detectron2's event
+    storage: returns (weighted dict, log dict with the floats the reference passes to put_scalar)."""
+    import math
+    out, log = {}, {}
+    idx = 0
+    for key, value in losses.items():
+        log[key + "_raw"] = value.detach().item()
+        tau = 1.0 if key == "loss_sem_seg" else 0.5
+        out[key] = tau * torch.exp(-log_vars[idx]) * value + 0.5 * log_vars[idx]
+        log[key + "_uncertainty"] = math.exp(log_vars[idx].detach().item())
+        idx = idx + 1
+    return out, log
