@@ -59,7 +59,7 @@ typedef struct MgvsProblem {
     float smoothing_weight;
     int automask;               /* automask_loss */
     int reduce_op;              /* 0 = "min" (the only one implemented) */
-    int padding_mode;           /* 0 = "zeros" (the only one implemented) */
+    int padding_mode;           /* grid_sample padding_mode (camera_utils.py:52-54): 0 = "zeros", 1 = "border", 2 = "reflection" */
     void *workspace;            /* >= mgvs_workspace_bytes(B,H,W,n) bytes, 256-byte aligned; must stay
                                    untouched between mgvs_forward and the matching mgvs_backward */
     size_t workspace_bytes;
@@ -141,6 +141,10 @@ int mgvs_backward(const MgvsProblem *p, const unsigned char *sel, const double *
 int mgvs_view_synthesis(int B, int H, int W, const float *ref_image, const float *depth, const float *camera,
                         long long cam_batch_stride, long long cam_row_stride, const float *pose34,
                         float *warped, float *coords /* [B,H,W,2] or NULL */, void *cuda_stream);
+/* Same with grid_sample's padding_mode (camera_utils.py:52-54): 0 zeros, 1 border, 2 reflection. */
+int mgvs_view_synthesis_ex(int B, int H, int W, const float *ref_image, const float *depth, const float *camera,
+                           long long cam_batch_stride, long long cam_row_stride, const float *pose34, int padding_mode,
+                           float *warped, float *coords /* [B,H,W,2] or NULL */, void *cuda_stream);
 
 /* Camera.reconstruct(depth, frame="c") (camera.py:107-136): points[B,3,H,W] = (K^-1 grid) * depth. */
 int mgvs_reconstruct(int B, int H, int W, const float *depth, const float *camera, long long cam_batch_stride,

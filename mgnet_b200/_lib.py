@@ -47,6 +47,7 @@ class MgvsProblem(ctypes.Structure):
 
 DGC_MAX_FILTER = 16
 MAX_LOSSES = 16
+PADDING_MODES = {"zeros": 0, "border": 1, "reflection": 2}
 PANOPTIC_NONE, PANOPTIC_I64, PANOPTIC_I32 = 0, 1, 2
 
 
@@ -145,6 +146,8 @@ def lib():
     L.mgvs_backward.argtypes = [PP, vp, vp, vp, ctypes.POINTER(vp), vp, vp]
     L.mgvs_view_synthesis.restype = ci
     L.mgvs_view_synthesis.argtypes = [ci, ci, ci, vp, vp, vp, ll, ll, vp, vp, vp, vp]
+    L.mgvs_view_synthesis_ex.restype = ci
+    L.mgvs_view_synthesis_ex.argtypes = [ci, ci, ci, vp, vp, vp, ll, ll, vp, ci, vp, vp, vp]
     L.mgvs_reconstruct.restype = ci
     L.mgvs_reconstruct.argtypes = [ci, ci, ci, vp, vp, ll, ll, vp, vp]
     L.mgvs_project.restype = ci
@@ -170,7 +173,7 @@ def lib():
 
 EXPORTED_SYMBOLS = (
     "mgvs_abi_version", "mgvs_last_error", "mgvs_num_sums", "mgvs_workspace_bytes", "mgvs_workspace_bytes_ex", "mgvs_stash_bytes", "mgvs_stash_bytes_ex", "mgvs_forward", "mgvs_forward_losses",
-    "mgvs_finalize", "mgvs_backward", "mgvs_view_synthesis", "mgvs_reconstruct", "mgvs_project", "mgvs_test_div",
+    "mgvs_finalize", "mgvs_backward", "mgvs_view_synthesis", "mgvs_view_synthesis_ex", "mgvs_reconstruct", "mgvs_project", "mgvs_test_div",
     "mgvs_dgc_workspace_bytes", "mgvs_dgc_rescale", "mgvs_dgc_heights",
     "mgvs_uncertainty_forward", "mgvs_uncertainty_backward",
 )

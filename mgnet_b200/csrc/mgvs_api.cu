@@ -445,7 +445,7 @@ __global__ void test_div_kernel(const float* a, const float* b, float* out, long
 // ---- standalone geometry primitives ------------------------------------------------------------
 __global__ void view_synthesis_kernel(int B, int H, int W, const float* __restrict__ ref, const float* __restrict__ depth,
                                       const float* __restrict__ camera, long long cbs, long long crs,
-                                      const float* __restrict__ pose34, float* __restrict__ warped, float* __restrict__ coords)
+                                      const float* __restrict__ pose34, float* __restrict__ warped, float* __restrict__ coords, int pad)
 {
     const int HW = H * W;
     long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -466,7 +466,7 @@ __global__ void view_synthesis_kernel(int B, int H, int W, const float* __restri
     for (int j = 0; j < 3; j++) Xc[j] = __fmul_rn(r[j], d);
     const float wm1 = (float)(W - 1), hm1 = (float)(H - 1);
     exact::Proj pr;
-    exact::project(K, Rt, Xc, wm1, hm1, exact::rcp_refined(wm1), exact::rcp_refined(hm1), pr);
+    exact::project<true>(K, Rt, Xc, wm1, hm1, exact::rcp_refined(wm1), exact::rcp_refined(hm1), pr, pad);
     exact::Cell c;
     exact::cell(pr.ix, pr.iy, H, W, c);
     float wnw = __fmul_rn(c.wN, c.wW), wne = __fmul_rn(c.wN, c.wE), wsw = __fmul_rn(c.wS, c.wW), wse = __fmul_rn(c.wS, c.wE);
@@ -607,7 +607,7 @@ static int check_problem(const MgvsProblem* p)
     if (!p->target || !p->source[0] || !p->source[1] || !p->camera || !p->poses) return fail(MGVS_EINVAL, "null input pointer");
     for (int i = 0; i < p->n; i++)
         if (!p->inv_depth[i]) return fail(MGVS_EINVAL, "null inverse-depth pointer");
-    if (p->padding_mode != 0) return fail(MGVS_EUNSUPPORTED, "padding_mode: only 'zeros' is implemented");
+    if (p->padding_mode < 0 || p->padding_mode > 2) return fail(MGVS_EINVAL, "padding_mode must be 0 (zeros), 1 (border) or 2 (reflection)");
     if (p->reduce_op != 0) return fail(MGVS_EUNSUPPORTED, "photometric_reduce_op: only 'min' is implemented");
     if (!(p->ssim_weight > 0.f)) return fail(MGVS_EUNSUPPORTED, "ssim_loss_weight must be > 0 (the L1-only branch of loss.py:195-196 is not implemented)");
     if (!p->workspace || ((uintptr_t)p->workspace & 255)) return fail(MGVS_EINVAL, "workspace null or not 256-byte aligned");
@@ -772,7 +772,7 @@ int mgvs_forward_losses(const MgvsProblem* p, unsigned char* sel, double* sums, 
     cudaMemsetAsync(ws + L.counter, 0, 256, st);   // arrival counter of reduce_kernel (workspace arrives uninitialised)
     FwdParams fp;
     memset(&fp, 0, sizeof(fp));
-    fp.B = p->B; fp.H = p->H; fp.W = p->W; fp.n = p->n; fp.automask = p->automask;
+    fp.B = p->B; fp.H = p->H; fp.W = p->W; fp.n = p->n; fp.automask = p->automask; fp.pad = p->padding_mode;
     fp.tgt = tgt_f; fp.src[0] = src_f[0]; fp.src[1] = src_f[1];
     for (int i = 0; i < p->n; i++) fp.inv[i] = p->inv_depth[i];
     fp.mask = p->mask; fp.cams = cams; fp.sel = sel;
@@ -813,8 +813,12 @@ int mgvs_forward_losses(const MgvsProblem* p, unsigned char* sel, double* sums, 
     fp.stash = (float4*)p->stash; fp.Wg = (p->W + 3) / 4;
     fp.wgt = p->stash ? (float*)((char*)p->stash + stash_texel_bytes(p->B, p->H, p->W, p->n)) : nullptr;
     {
-        void (*kern)(FwdParams, FwdMaps) = use_tma ? (p->stash ? fwd_kernel<true, true> : fwd_kernel<true, false>)
-                                                   : (p->stash ? fwd_kernel<false, true> : fwd_kernel<false, false>);
+        // padding_mode "zeros" runs the PAD = false instantiations (unchanged code); "border" / "reflection" the PAD = true ones
+        void (*kern)(FwdParams, FwdMaps) =
+            p->padding_mode == 0 ? (use_tma ? (p->stash ? fwd_kernel<true, true> : fwd_kernel<true, false>)
+                                            : (p->stash ? fwd_kernel<false, true> : fwd_kernel<false, false>))
+                                 : (use_tma ? (p->stash ? fwd_kernel<true, true, true> : fwd_kernel<true, false, true>)
+                                            : (p->stash ? fwd_kernel<false, true, true> : fwd_kernel<false, false, true>));
         cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, FWD_SMEM_BYTES);
         launch_pdl(kern, dim3(L.tiles), dim3(NT), FWD_SMEM_BYTES, st, fp, maps);
     }
@@ -855,7 +859,7 @@ int mgvs_backward(const MgvsProblem* p, const unsigned char* sel, const double* 
         // stash backward: box adjoint of the forward's coefficient texels + per-output chain (mgvs_bwd_stash.cuh)
         BwdSParams sp;
         memset(&sp, 0, sizeof(sp));
-        sp.B = p->B; sp.H = p->H; sp.W = p->W; sp.n = p->n; sp.automask = p->automask;
+        sp.B = p->B; sp.H = p->H; sp.W = p->W; sp.n = p->n; sp.automask = p->automask; sp.pad = p->padding_mode;
         sp.tgt = tgt_f;
         const int lowres = lowres_mode(p);
         // fused upsample: the kernel writes full-resolution gradients into the stash tail, the adjoint kernel folds them
@@ -892,7 +896,8 @@ int mgvs_backward(const MgvsProblem* p, const unsigned char* sel, const double* 
             tma_img = make_map(&smaps.tgt, tgt_f, 3 * p->B, p->H, p->W, BS_ROWS, 3);
             for (int i = 0; i < p->n && tma_img && !lowres; i++) tma_img = make_map(&smaps.inv[i], p->inv_depth[i], p->B, p->H, p->W, BS_ROWS, 1);
         }
-        void (*kern)(BwdSParams, BwdSMaps) = tma_img ? bwd_stash_kernel<true> : bwd_stash_kernel<false>;
+        void (*kern)(BwdSParams, BwdSMaps) = p->padding_mode == 0 ? (tma_img ? bwd_stash_kernel<true> : bwd_stash_kernel<false>)
+                                                                  : (tma_img ? bwd_stash_kernel<true, true> : bwd_stash_kernel<false, true>);
         cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, BS_SMEM_BYTES);
         kern<<<L.tiles, NT, BS_SMEM_BYTES, st>>>(sp, smaps);
         pose_reduce_kernel<<<p->B * S, 128, 0, st>>>(L.tiles_x * L.tiles_y, sp.pose_partials, p->poses, grad_poses);
@@ -907,7 +912,7 @@ int mgvs_backward(const MgvsProblem* p, const unsigned char* sel, const double* 
     }
     BwdParams bp;
     memset(&bp, 0, sizeof(bp));
-    bp.B = p->B; bp.H = p->H; bp.W = p->W; bp.n = p->n; bp.automask = p->automask;
+    bp.B = p->B; bp.H = p->H; bp.W = p->W; bp.n = p->n; bp.automask = p->automask; bp.pad = p->padding_mode;
     bp.tgt = tgt_f; bp.src[0] = src_f[0]; bp.src[1] = src_f[1];
     for (int i = 0; i < p->n; i++) {
         bp.inv[i] = p->inv_depth[i];
@@ -927,27 +932,34 @@ int mgvs_backward(const MgvsProblem* p, const unsigned char* sel, const double* 
         use_tma = make_map(&maps.tgt, tgt_f, 3 * p->B, p->H, p->W, BWD_ROWS, 3);
         for (int i = 0; i < p->n && use_tma; i++) use_tma = make_map(&maps.inv[i], p->inv_depth[i], p->B, p->H, p->W, BWD_ROWS, 1);
     }
-    if (use_tma) {
-        cudaFuncSetAttribute(bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, BWD_SMEM_BYTES);
-        bwd_kernel<true><<<L.tiles, NT, BWD_SMEM_BYTES, st>>>(bp, maps);
-    } else {
-        memset(&maps, 0, sizeof(maps));
-        cudaFuncSetAttribute(bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, BWD_SMEM_BYTES);
-        bwd_kernel<false><<<L.tiles, NT, BWD_SMEM_BYTES, st>>>(bp, maps);
+    if (!use_tma) memset(&maps, 0, sizeof(maps));
+    {
+        void (*kern)(BwdParams, BwdMaps) = p->padding_mode == 0 ? (use_tma ? bwd_kernel<true> : bwd_kernel<false>)
+                                                                : (use_tma ? bwd_kernel<true, true> : bwd_kernel<false, true>);
+        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, BWD_SMEM_BYTES);
+        kern<<<L.tiles, NT, BWD_SMEM_BYTES, st>>>(bp, maps);
     }
     pose_reduce_kernel<<<p->B * S, 128, 0, st>>>(L.tiles_x * L.tiles_y, bp.pose_partials, p->poses, grad_poses);
     return check_launch("mgvs_backward");
+}
+
+int mgvs_view_synthesis_ex(int B, int H, int W, const float* ref_image, const float* depth, const float* camera,
+                           long long cam_batch_stride, long long cam_row_stride, const float* pose34, int padding_mode,
+                           float* warped, float* coords, void* cuda_stream)
+{
+    if (B < 1 || H < 2 || W < 2 || !ref_image || !depth || !camera || !pose34 || !warped) return fail(MGVS_EINVAL, "bad argument");
+    if (padding_mode < 0 || padding_mode > 2) return fail(MGVS_EINVAL, "padding_mode must be 0 (zeros), 1 (border) or 2 (reflection)");
+    long long total = (long long)B * H * W;
+    view_synthesis_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)cuda_stream>>>(
+        B, H, W, ref_image, depth, camera, cam_batch_stride, cam_row_stride, pose34, warped, coords, padding_mode);
+    return check_launch("mgvs_view_synthesis");
 }
 
 int mgvs_view_synthesis(int B, int H, int W, const float* ref_image, const float* depth, const float* camera,
                         long long cam_batch_stride, long long cam_row_stride, const float* pose34, float* warped,
                         float* coords, void* cuda_stream)
 {
-    if (B < 1 || H < 2 || W < 2 || !ref_image || !depth || !camera || !pose34 || !warped) return fail(MGVS_EINVAL, "bad argument");
-    long long total = (long long)B * H * W;
-    view_synthesis_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)cuda_stream>>>(
-        B, H, W, ref_image, depth, camera, cam_batch_stride, cam_row_stride, pose34, warped, coords);
-    return check_launch("mgvs_view_synthesis");
+    return mgvs_view_synthesis_ex(B, H, W, ref_image, depth, camera, cam_batch_stride, cam_row_stride, pose34, 0, warped, coords, cuda_stream);
 }
 
 int mgvs_reconstruct(int B, int H, int W, const float* depth, const float* camera, long long cam_batch_stride,

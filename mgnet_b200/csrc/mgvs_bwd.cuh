@@ -21,6 +21,7 @@ namespace mgvs {
 
 struct BwdParams {
     int B, H, W, n, automask;
+    int pad;                      // padding_mode of the PAD kernels (1 border, 2 reflection)
     const float* tgt;
     const float* src[S];
     const float* inv[MAXN];
@@ -101,7 +102,7 @@ __device__ __forceinline__ void box_adjoint4(const float4* __restrict__ mp, cons
             }
 }
 
-template <bool USE_TMA>
+template <bool USE_TMA, bool PAD = false>
 __global__ void __launch_bounds__(NT, MIN_CTAS) bwd_kernel(const BwdParams p, const __grid_constant__ BwdMaps maps)
 {
     extern __shared__ __align__(128) float smem[];
@@ -289,8 +290,8 @@ __global__ void __launch_bounds__(NT, MIN_CTAS) bwd_kernel(const BwdParams p, co
         }
         // ---- stage A: warp both sources on tile+2 (software pipelined, mgvs_device.cuh) ----
 #ifndef MGVS_SKIP_A
-        warp_tile<2, BWD_ROWS, BWD_CH, USE_TMA>(sX, sX + 3 * BWD_CH, sI, inv, src0, src1, sCam, x0, y0, H, W, border,
-                                                 wm1, hm1, rw, rh, tid);
+        warp_tile<2, BWD_ROWS, BWD_CH, USE_TMA, PAD>(sX, sX + 3 * BWD_CH, sI, inv, src0, src1, sCam, x0, y0, H, W, border,
+                                                      wm1, hm1, rw, rh, tid, p.pad);
 #endif
         __syncthreads();
 
@@ -434,7 +435,7 @@ __global__ void __launch_bounds__(NT, MIN_CTAS) bwd_kernel(const BwdParams p, co
 #pragma unroll
                 for (int j = 0; j < 3; j++) Xc[j] = __fmul_rn(r[j], d);
                 exact::Proj pr;
-                exact::project(K, Rt, Xc, wm1, hm1, rw, rh, pr);
+                exact::project<PAD>(K, Rt, Xc, wm1, hm1, rw, rh, pr, p.pad);
                 // bilinear adjoint (GridSampler backward w.r.t. the grid): out-of-image corners are zeros of the border
                 float xw = floorf(pr.ix), yn = floorf(pr.iy);
                 float wE = pr.ix - xw, wW = 1.0f - wE, wS = pr.iy - yn, wN = 1.0f - wS;
@@ -445,6 +446,7 @@ __global__ void __launch_bounds__(NT, MIN_CTAS) bwd_kernel(const BwdParams p, co
                             g2 * ((ne.z - nw.z) * wN + (se.z - sw.z) * wS);
                 float giy = g0 * ((sw.x - nw.x) * wW + (se.x - ne.x) * wE) + g1 * ((sw.y - nw.y) * wW + (se.y - ne.y) * wE) +
                             g2 * ((sw.z - nw.z) * wW + (se.z - ne.z) * wE);
+                if constexpr (PAD) { gix *= pr.mx; giy *= pr.my; }   // padding-mode derivative (clip / reflect)
                 // projection adjoint (App. B-5)
                 float iz = exact::rcp_refined(pr.Z);
                 float gP0 = gix * iz, gP1 = giy * iz;

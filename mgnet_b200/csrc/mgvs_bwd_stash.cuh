@@ -28,6 +28,7 @@ namespace mgvs {
 
 struct BwdSParams {
     int B, H, W, n, automask;
+    int pad;                      // padding_mode of the PAD kernels (1 border, 2 reflection)
     const float* tgt;
     const float* inv[MAXN];
     const unsigned char* mask;
@@ -151,7 +152,7 @@ __device__ __forceinline__ float signed_const(float cf, float d)
 constexpr int BS_SX = 64;                  // thread layout of the stash backward: 64 columns x 4 strips of 4 rows
 // (assumes the 64x16 tile / 256 threads of the product build; mgvs_api.cu refuses the stash path otherwise)
 
-template <bool USE_TMA>
+template <bool USE_TMA, bool PAD = false>
 __global__ void __launch_bounds__(NT, MIN_CTAS) bwd_stash_kernel(const __grid_constant__ BwdSParams p, const __grid_constant__ BwdSMaps maps)
 {
     extern __shared__ __align__(128) float smem[];
@@ -380,7 +381,7 @@ __global__ void __launch_bounds__(NT, MIN_CTAS) bwd_stash_kernel(const __grid_co
 #pragma unroll
                 for (int j = 0; j < 3; j++) Xc[j] = __fmul_rn(r[j], d);
                 exact::Proj pr;
-                exact::project(Kf, Rtf, Xc, wm1, hm1, rw, rh, pr);
+                exact::project<PAD>(Kf, Rtf, Xc, wm1, hm1, rw, rh, pr, p.pad);
                 // same footprint arithmetic as the forward (mgvs_device.cuh footprint/blend4): x_q comes out bit-identical
                 float xw = floorf(pr.ix), yn = floorf(pr.iy);
                 float wE = __fadd_rn(pr.ix, -xw), wW = __fadd_rn(1.0f, -wE), wS = __fadd_rn(pr.iy, -yn), wN = __fadd_rn(1.0f, -wS);
@@ -402,6 +403,7 @@ __global__ void __launch_bounds__(NT, MIN_CTAS) bwd_stash_kernel(const __grid_co
                             g[2] * ((ne.z - nw.z) * wN + (se.z - sw.z) * wS);
                 float giy = g[0] * ((sw.x - nw.x) * wW + (se.x - ne.x) * wE) + g[1] * ((sw.y - nw.y) * wW + (se.y - ne.y) * wE) +
                             g[2] * ((sw.z - nw.z) * wW + (se.z - ne.z) * wE);
+                if constexpr (PAD) { gix *= pr.mx; giy *= pr.my; }   // padding-mode derivative (clip / reflect)
                 // projection adjoint (App. B-5)
                 float iz = exact::rcp_refined(pr.Z);
                 float gP0 = gix * iz, gP1 = giy * iz;

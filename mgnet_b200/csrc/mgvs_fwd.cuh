@@ -16,6 +16,7 @@ namespace mgvs {
 
 struct FwdParams {
     int B, H, W, n, automask;
+    int pad;                     // grid_sample padding_mode for the PAD kernels: 1 border, 2 reflection (0 = zeros: PAD = false kernels)
     int early_wait;              // the image pointers are workspace copies written by the preceding kernel (uint8 ingestion)
     const float* tgt;
     const float* src[S];
@@ -134,7 +135,7 @@ __device__ __forceinline__ void photometric4(const float* __restrict__ xs, const
         out[k] = __fadd_rn(__fmul_rn(alpha, exact::div3(ssum[k])), __fmul_rn(oma, exact::div3(lsum[k])));
 }
 
-template <bool USE_TMA, bool STASH>
+template <bool USE_TMA, bool STASH, bool PAD = false>
 __global__ void __launch_bounds__(NT, MIN_CTAS) fwd_kernel(const FwdParams p, const __grid_constant__ FwdMaps maps)
 {
     extern __shared__ __align__(128) float smem[];
@@ -321,8 +322,8 @@ __global__ void __launch_bounds__(NT, MIN_CTAS) fwd_kernel(const FwdParams p, co
             tma::mbar_wait(sBar + 1 + (i & 1), (i >> 1) & 1);
         }
         // ---- stage 1: warp both sources at every halo pixel (software pipelined, mgvs_device.cuh) ----
-        warp_tile<1, FWD_ROWS, FWD_CH, USE_TMA>(sX, sX + FWD_TILE3_FLOATS, sI, inv, src0, src1, sCam, x0, y0, H, W, border,
-                                                 wm1, hm1, rw, rh, tid);
+        warp_tile<1, FWD_ROWS, FWD_CH, USE_TMA, PAD>(sX, sX + FWD_TILE3_FLOATS, sI, inv, src0, src1, sCam, x0, y0, H, W, border,
+                                                      wm1, hm1, rw, rh, tid, p.pad);
         __syncthreads();
 
         // ---- stage 2: photometric maps, min/argmin, smoothness ----

@@ -30,8 +30,10 @@ def _stream(t):
 
 def view_synthesis(ref_image, depth, ref_cam, cam, mode="bilinear", padding_mode="zeros", return_coords=False):
     assert depth.size(1) == 1
-    if mode != "bilinear" or padding_mode != "zeros":
-        raise NotImplementedError("view_synthesis kernel implements mode='bilinear', padding_mode='zeros' only")
+    if mode != "bilinear":
+        raise NotImplementedError("view_synthesis kernel implements mode='bilinear' only")
+    if padding_mode not in _lib.PADDING_MODES:
+        raise ValueError("padding_mode must be 'zeros', 'border' or 'reflection', got %r" % (padding_mode,))
     if not (ref_image.is_cuda and depth.is_cuda):
         raise RuntimeError("view_synthesis runs only on CUDA (sm_100a); there is no CPU fallback")
     B, _, H, W = depth.shape
@@ -47,7 +49,7 @@ def view_synthesis(ref_image, depth, ref_cam, cam, mode="bilinear", padding_mode
     warped = torch.empty_like(ref_image)
     coords = torch.empty(B, H, W, 2, device=depth.device, dtype=torch.float32) if return_coords else None
     with torch.cuda.device(depth.device):
-        _lib.check(_lib.lib().mgvs_view_synthesis(
+        _lib.check(_lib.lib().mgvs_view_synthesis_ex(
             B, H, W, ref_image.data_ptr(), depth.data_ptr(), K.data_ptr(), K.stride(0), K.stride(1), pose34.data_ptr(),
-            warped.data_ptr(), coords.data_ptr() if coords is not None else None, _stream(depth)), "mgvs_view_synthesis")
+            _lib.PADDING_MODES[padding_mode], warped.data_ptr(), coords.data_ptr() if coords is not None else None, _stream(depth)), "mgvs_view_synthesis")
     return (warped, coords) if return_coords else warped

@@ -50,8 +50,8 @@ class MultiViewPhotometricLoss(nn.Module):
             assert self.photometric_reduce_op == "min", \
                 "For automasking only the min photometric_reduce_op is supported."
         # legal-but-unimplemented combinations fail loudly at construction time
-        if padding_mode != "zeros":
-            raise NotImplementedError("padding_mode=%r: the fused kernels implement 'zeros' only" % (padding_mode,))
+        if padding_mode not in ("zeros", "border", "reflection"):   # what F.grid_sample accepts (camera_utils.py:52-54)
+            raise ValueError("padding_mode must be 'zeros', 'border' or 'reflection', got %r" % (padding_mode,))
         if photometric_reduce_op not in ("min", "mean"):
             raise NotImplementedError("Unknown photometric_reduce_op: {}".format(photometric_reduce_op))
         if photometric_reduce_op == "mean":

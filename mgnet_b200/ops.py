@@ -98,7 +98,7 @@ def _fill_problem(prob, cfg, tgt, prev, nxt, inv, camera, poses, mask, ws, stash
     prob.smoothing_weight = float(cfg.smoothing_loss_weight)
     prob.automask = int(bool(cfg.automask_loss))
     prob.reduce_op = 0
-    prob.padding_mode = 0
+    prob.padding_mode = _lib.PADDING_MODES[cfg.padding_mode]
     prob.workspace = ws.data_ptr()
     prob.workspace_bytes = ws.numel()
     prob.stash = stash.data_ptr() if stash is not None else None
@@ -117,8 +117,8 @@ class _ViewSynthesisLoss(torch.autograd.Function):
             if cfg.photometric_reduce_op == "mean":
                 raise NotImplementedError("photometric_reduce_op='mean' is not implemented by the fused kernels")
             raise NotImplementedError("Unknown photometric_reduce_op: {}".format(cfg.photometric_reduce_op))
-        if cfg.padding_mode != "zeros":
-            raise NotImplementedError("padding_mode=%r is not implemented by the fused kernels (only 'zeros')" % (cfg.padding_mode,))
+        if cfg.padding_mode not in _lib.PADDING_MODES:
+            raise ValueError("padding_mode must be 'zeros', 'border' or 'reflection', got %r" % (cfg.padding_mode,))
         n = len(inv)
         if n < 1 or n > _lib.MAX_SCALES:
             raise ValueError("need 1..%d inverse-depth maps, got %d" % (_lib.MAX_SCALES, n))

@@ -44,6 +44,7 @@ typedef struct {
     const uint8_t *mask;            /* [B,1,H,W] bool or NULL */
     float ssim_w, photo_w, smooth_w;
     int automask;
+    int padding_mode;               /* grid_sample padding_mode (camera_utils.py:52-54): 0 zeros, 1 border, 2 reflection */
 } OrcIn;
 
 typedef struct {
@@ -133,11 +134,34 @@ typedef struct { /* everything the projection of one pixel produces (fp32, refer
     float P[3];   /* K Xs */
     float Z, ax, ay; /* clamp(Pz), Px/Z, Py/Z */
     float xn, yn; /* normalised coords */
-    float ix, iy; /* un-normalised sample position (ATen GridSampler.h:27-36) */
+    float ix, iy; /* sample position in source pixels after the padding-mode mapping (ATen GridSampler.h:27-36, 60-140) */
+    float mx, my; /* d(ix)/d(un-normalised x), d(iy)/d(un-normalised y): 1 for zeros; 0 / +-1 for border / reflection */
 } OrcProj;
 
+/* grid_sampler_compute_source_index for align_corners=True (ATen GridSampler.h:60-140; CPU vectorised kernel
+ * GridSamplerKernel.cpp ComputeLocation): border clips to [0, size-1]; reflection folds around 0 and size-1
+ * (|c| - trunc(|c| / 2span) * 2span, then min(extra, 2span - extra)) and clips.  Probed bit for bit against torch 2.11.
+ * *mult receives the derivative the backward applies (clip_coordinates_set_grad / reflect_coordinates_set_grad). */
+static inline float orc_pad_coord(float c, float sm1, int mode, float *mult)
+{
+    *mult = 1.0f;
+    if (mode == 0) return c;
+    if (mode == 2) {
+        float ts = sm1 + sm1, a = fabsf(c);
+        float df = truncf(a / ts);
+        float extra = a - df * ts;
+        float other = ts - extra;
+        float sgn = c < 0.0f ? -1.0f : 1.0f;
+        *mult = extra <= other ? sgn : -sgn;
+        c = extra < other ? extra : other;
+    }
+    if (!(c > 0.0f && c < sm1)) *mult = 0.0f;
+    float lo = c > 0.0f ? c : 0.0f;
+    return lo < sm1 ? lo : sm1;
+}
+
 static inline void orc_project(const float K[9], const float Kinv[9], const float Rt[12], int u, int v,
-                               float inv, int H, int W, OrcProj *o)
+                               float inv, int H, int W, int pad, OrcProj *o)
 {
     float gu = (float)u, gv = (float)v;
     for (int j = 0; j < 3; j++) o->r[j] = dot3(Kinv[j * 3], Kinv[j * 3 + 1], Kinv[j * 3 + 2], gu, gv, 1.0f);
@@ -157,6 +181,8 @@ static inline void orc_project(const float K[9], const float Kinv[9], const floa
     o->yn = (2.0f * o->ay) / hm1 - 1.0f;
     o->ix = (o->xn + 1.0f) * (wm1 * 0.5f);           /* ((c+1)/2)*(size-1) == (c+1)*((size-1)/2) */
     o->iy = (o->yn + 1.0f) * (hm1 * 0.5f);
+    o->ix = orc_pad_coord(o->ix, wm1, pad, &o->mx);
+    o->iy = orc_pad_coord(o->iy, hm1, pad, &o->my);
 }
 
 typedef struct {
@@ -259,7 +285,7 @@ static void orc_warp(const OrcIn *in, int b, int i, int s, const float K[9], con
     for (int v = 0; v < H; v++)
         for (int u = 0; u < W; u++) {
             OrcProj p; OrcCell c; float vals[4];
-            orc_project(K, Kinv, Rt, u, v, inv[(long)v * W + u], H, W, &p);
+            orc_project(K, Kinv, Rt, u, v, inv[(long)v * W + u], H, W, in->padding_mode, &p);
             orc_cell(p.ix, p.iy, H, W, &c);
             for (int ch = 0; ch < 3; ch++) warped[ch * HW + (long)v * W + u] = orc_bilinear(src + ch * HW, W, &c, vals);
             if (coords) { coords[((long)v * W + u) * 2] = p.xn; coords[((long)v * W + u) * 2 + 1] = p.yn; }
@@ -566,7 +592,7 @@ int orc_backward(const OrcIn *in, double ssim_w_double, int euler_fma, const uin
                             }
                             if (!any) continue;
                             OrcProj pr; OrcCell c; float vals[4];
-                            orc_project(K, Kinv, Rt[s], u, v, inv[q], H, W, &pr);
+                            orc_project(K, Kinv, Rt[s], u, v, inv[q], H, W, in->padding_mode, &pr);
                             orc_cell(pr.ix, pr.iy, H, W, &c);
                             double gix = 0, giy = 0;
                             for (int ch = 0; ch < 3; ch++) {
@@ -575,6 +601,8 @@ int orc_backward(const OrcIn *in, double ssim_w_double, int euler_fma, const uin
                                 gix += G[ch] * ((ne - nw) * (double)c.wN + (se - sw) * (double)c.wS);
                                 giy += G[ch] * ((sw - nw) * (double)c.wW + (se - ne) * (double)c.wE);
                             }
+                            gix *= (double)pr.mx;   /* padding-mode derivative (1 for zeros) */
+                            giy *= (double)pr.my;
                             double Z = pr.Z;
                             double gP[3] = {gix / Z, giy / Z, 0.0};
                             if (pr.P[2] >= 1e-5f) gP[2] = -(gix * (double)pr.ax + giy * (double)pr.ay) / Z;

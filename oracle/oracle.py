@@ -52,6 +52,7 @@ class _OrcIn(ctypes.Structure):
         ("mask", ctypes.c_void_p),
         ("ssim_w", ctypes.c_float), ("photo_w", ctypes.c_float), ("smooth_w", ctypes.c_float),
         ("automask", ctypes.c_int),
+        ("padding_mode", ctypes.c_int),
     ]
 
 
@@ -102,7 +103,7 @@ class Oracle:
     EULER_FMA = 0
 
     def __init__(self, predictions, targets, ssim_loss_weight=0.85, photometric_loss_weight=1.0,
-                 smoothing_loss_weight=1e-3, automask_loss=True):
+                 smoothing_loss_weight=1e-3, automask_loss=True, padding_mode="zeros"):
         self.inv = [_np(d) for d in predictions["depth"]]
         self.n = len(self.inv)
         self.B, _, self.H, self.W = self.inv[0].shape
@@ -131,6 +132,7 @@ class Oracle:
         i.mask = _ptr(self.mask) if self.mask is not None else None
         i.ssim_w, i.photo_w, i.smooth_w = self.ssim_w, self.photo_w, self.smooth_w
         i.automask = int(self.automask)
+        i.padding_mode = {"zeros": 0, "border": 1, "reflection": 2}[padding_mode]
         self.sums = None
         self.sel = None
 

@@ -75,7 +75,7 @@ def _kinv(K):
     return Ki
 
 
-def _synthesize(src, depth, K, Ki, T_src, T_tgt_inv):
+def _synthesize(src, depth, K, Ki, T_src, T_tgt_inv, padding_mode="zeros"):
     """view_synthesis (camera_utils.py:24-54) = reconstruct("w") -> project("w") -> grid_sample."""
     B, _, H, W = depth.shape
     rays = Ki.bmm(_pixel_grid(B, H, W, depth.dtype, depth.device)).view(B, 3, H, W)
@@ -85,7 +85,7 @@ def _synthesize(src, depth, K, Ki, T_src, T_tgt_inv):
     xn = 2 * (X / Z) / (W - 1) - 1.0
     yn = 2 * (Y / Z) / (H - 1) - 1.0
     coords = torch.stack([xn, yn], dim=-1).view(B, H, W, 2)
-    return F.grid_sample(src, coords, mode="bilinear", padding_mode="zeros", align_corners=True)
+    return F.grid_sample(src, coords, mode="bilinear", padding_mode=padding_mode, align_corners=True)
 
 
 def _ssim(x, y, c1=1e-4, c2=9e-4):
@@ -105,7 +105,7 @@ def _photometric(est, tgt, w_ssim):
 
 
 def reference_loss(predictions, targets, ssim_loss_weight=0.85, photometric_loss_weight=1.0,
-                   smoothing_loss_weight=1e-3, automask_loss=True, return_selection=False):
+                   smoothing_loss_weight=1e-3, automask_loss=True, return_selection=False, padding_mode="zeros"):
     """Same dictionaries in, same dictionary out as the reference's forward (loss.py:111-154)."""
     inv = predictions["depth"]
     n = len(inv)
@@ -120,7 +120,7 @@ def reference_loss(predictions, targets, ssim_loss_weight=0.85, photometric_loss
     for s, src in enumerate(sources):
         T = _pose44(poses[:, s].float())
         for i in range(n):
-            maps[i].append(_photometric(_synthesize(src, depths[i], K, Ki, T, ident_inv), tgt, ssim_loss_weight))
+            maps[i].append(_photometric(_synthesize(src, depths[i], K, Ki, T, ident_inv, padding_mode), tgt, ssim_loss_weight))
             if i == 0 and automask_loss:
                 ident = _photometric(src, tgt, ssim_loss_weight)
             if automask_loss:

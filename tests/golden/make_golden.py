@@ -34,6 +34,10 @@ CASES = {
     "automask_off": (dict(B=1, H=32, W=64, n=2, seed=5, noise=0.2), {"automask_loss": False}, False),
     "weights_alpha": (dict(B=1, H=36, W=68, n=2, seed=6, noise=0.0, shift_sources=True),
                       {"ssim_loss_weight": 0.5, "photometric_loss_weight": 2.0, "smoothing_loss_weight": 0.05}, False),
+    # grid_sample padding modes (camera_utils.py:52-54; config.py:116-117): large poses push many samples outside the image
+    "pad_border": (dict(B=2, H=40, W=72, n=2, seed=9, noise=0.1, pose_scale=0.06), {"padding_mode": "border"}, True),
+    "pad_reflection": (dict(B=2, H=40, W=72, n=2, seed=10, noise=0.0, pose_scale=0.06, shift_sources=True),
+                       {"padding_mode": "reflection"}, True),
 }
 
 
@@ -51,11 +55,24 @@ def adversarial(pred, tgt):
     return pred, tgt
 
 
-def main():
+def far_out(pred):
+    """pad_*: one source far outside the image (several reflections), one behind the camera."""
+    poses = pred["poses"].clone()
+    poses[1, 1] = torch.tensor([3.0, 0.5, 0.2, 0.0, 0.02, 0.3])
+    poses[0, 0] = torch.tensor([-0.8, 0.1, -0.3, 0.05, -0.2, 0.01])
+    pred["poses"] = snap_pose_trig(poses)
+    return pred
+
+
+def main(only=None):
     for name, (kw, hp_over, keep) in CASES.items():
+        if only and name not in only:
+            continue
         pred, tgt = make_inputs(**kw)
         if name == "ragged_n4_bigpose":
             pred, tgt = adversarial(pred, tgt)
+        if name.startswith("pad_"):
+            pred = far_out(pred)
         hp = dict(ref_loader.DEFAULT_HP)
         hp.update(hp_over)
         res = ref_loader.run_reference(pred, tgt, hp=hp, want_grads=True, want_intermediates=True)
@@ -70,6 +87,7 @@ def main():
             "hp_photometric_loss_weight": np.float64(hp["photometric_loss_weight"]),
             "hp_smoothing_loss_weight": np.float64(hp["smoothing_loss_weight"]),
             "hp_automask_loss": np.bool_(hp["automask_loss"]),
+            "hp_padding_mode": np.array(hp["padding_mode"]),
             "loss_photometric": res["loss_photometric"],
             "loss_smoothness": res["loss_smoothness"],
             "grad_poses": res["grad_poses"],
@@ -131,6 +149,8 @@ if __name__ == "__main__":
     torch.set_num_threads(1)   # the reference on CPU is thread-count independent; be safe
     if len(sys.argv) > 1 and sys.argv[1] == "fused":
         make_fused_upsample()      # leaves the other (committed) fixtures untouched
+    elif len(sys.argv) > 1:
+        main(only=sys.argv[1:])    # e.g. `make_golden.py pad_border pad_reflection`
     else:
         main()
         make_fused_upsample()

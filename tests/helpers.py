@@ -43,7 +43,7 @@ def load_golden(name):
         smoothing_loss_weight=float(z["hp_smoothing_loss_weight"]),
         automask_loss=bool(z["hp_automask_loss"]),
         photometric_reduce_op="min",
-        padding_mode="zeros",
+        padding_mode=str(z["hp_padding_mode"]) if "hp_padding_mode" in z.files else "zeros",
     )
     ref = {k: z[k] for k in z.files if not k.startswith("in_") and not k.startswith("hp_")}
     return pred, tgt, hp, ref

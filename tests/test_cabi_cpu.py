@@ -56,8 +56,10 @@ def test_struct_layout_matches_header():
 
 def test_module_rejects_unsupported_configs_loudly():
     from mgnet_b200 import MultiViewPhotometricLoss
-    with pytest.raises(NotImplementedError):
-        MultiViewPhotometricLoss(0.85, 1.0, 1e-3, True, "min", "border")
+    with pytest.raises(ValueError):
+        MultiViewPhotometricLoss(0.85, 1.0, 1e-3, True, "min", "mirror")       # not a grid_sample padding mode
+    for mode in ("zeros", "border", "reflection"):                             # all three of the reference's are implemented
+        MultiViewPhotometricLoss(0.85, 1.0, 1e-3, True, "min", mode)
     with pytest.raises(AssertionError):
         MultiViewPhotometricLoss(0.85, 1.0, 1e-3, True, "mean", "zeros")
     with pytest.raises(NotImplementedError):

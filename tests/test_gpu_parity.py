@@ -15,7 +15,7 @@ from helpers import GRAD_RTOL, LOSS_RTOL, golden_names, l2rel, load_golden, maxr
 
 pytestmark = pytest.mark.gpu
 
-OR_KEYS = ("ssim_loss_weight", "photometric_loss_weight", "smoothing_loss_weight", "automask_loss")
+OR_KEYS = ("ssim_loss_weight", "photometric_loss_weight", "smoothing_loss_weight", "automask_loss", "padding_mode")
 
 
 def _dev():
@@ -53,7 +53,7 @@ def test_library_loaded_is_in_tree():
     _dev()
     from mgnet_b200 import _lib
     L = _lib.lib()
-    assert L.mgvs_abi_version() == 4
+    assert L.mgvs_abi_version() == 5
     assert _lib.LIB_PATH.endswith("mgnet_b200/libmgvs.so")
 
 
@@ -83,16 +83,19 @@ def test_golden_backward(name, backward):
 
 
 @pytest.mark.parametrize("backward", BACKWARDS)
-@pytest.mark.parametrize("shape", [(2, 192, 640, 3, 0.2, False), (1, 96, 320, 4, 0.0, True), (3, 50, 70, 2, 0.2, False)])
+@pytest.mark.parametrize("shape", [(2, 192, 640, 3, 0.2, False, "zeros", 0.01), (1, 96, 320, 4, 0.0, True, "zeros", 0.01),
+                                   (3, 50, 70, 2, 0.2, False, "zeros", 0.01), (2, 192, 640, 3, 0.0, True, "border", 0.05),
+                                   (2, 96, 320, 2, 0.2, False, "reflection", 0.05), (2, 50, 70, 2, 0.0, True, "reflection", 0.08)])
 def test_against_oracle(shape, backward):
-    """Sizes the oracle finishes in seconds, incl. H/W that are not multiples of the 64x16 tile."""
+    """Sizes the oracle finishes in seconds, incl. H/W that are not multiples of the 64x16 tile and grid_sample's
+    border / reflection padding with poses large enough to push many samples outside the image."""
     dev = _dev()
     from mgnet_b200.synthetic import make_inputs
     from oracle.oracle import Oracle
-    B, H, W, n, noise, shift = shape
-    pred, tgt = make_inputs(B, H, W, n, seed=11, noise=noise, shift_sources=shift)
+    B, H, W, n, noise, shift, pad, pose_scale = shape
+    pred, tgt = make_inputs(B, H, W, n, seed=11, noise=noise, shift_sources=shift, pose_scale=pose_scale)
     hp = dict(ssim_loss_weight=0.85, photometric_loss_weight=1.0, smoothing_loss_weight=1e-3, automask_loss=True,
-              photometric_reduce_op="min", padding_mode="zeros")
+              photometric_reduce_op="min", padding_mode=pad)
     o = Oracle(pred, tgt, **{k: hp[k] for k in OR_KEYS})
     f = o.forward()
     g = o.backward(1.0, 1.0)
@@ -147,17 +150,19 @@ def test_exact_division_matches_ieee():
         assert int((out != ref).sum()) == 0
 
 
-def test_view_synthesis_matches_reference_intermediates():
+@pytest.mark.parametrize("fixture", ["kitti_small_mask", "pad_border", "pad_reflection"])
+def test_view_synthesis_matches_reference_intermediates(fixture):
     dev = _dev()
     from mgnet_b200.geometry import Camera, Pose, inv2depth, view_synthesis
-    pred, tgt, hp, ref = load_golden("kitti_small_mask")
+    pred, tgt, hp, ref = load_golden(fixture)
     K = tgt["camera_matrix"][:, :3, :3].to(dev)
     for s, key in enumerate(("image_prev_orig", "image_next_orig")):
         pose = Pose.from_vec(pred["poses"][:, s].to(dev), "euler")
         # the pose matrix itself must match the reference's bit for bit (trig boundary: snapped angles)
         depth = inv2depth(pred["depth"][0].to(dev))
         pose_ref = Pose(torch.from_numpy(ref["pose_mat"][:, s]).to(dev))
-        warped, coords = view_synthesis(tgt[key].to(dev), depth, Camera(K, Tcw=pose_ref), Camera(K).to(dev), return_coords=True)
+        warped, coords = view_synthesis(tgt[key].to(dev), depth, Camera(K, Tcw=pose_ref), Camera(K).to(dev),
+                                        padding_mode=hp["padding_mode"], return_coords=True)
         assert np.array_equal(coords.cpu().numpy(), ref["coords_0_%d" % s])
         assert np.array_equal(warped.cpu().numpy(), ref["warped_0_%d" % s])
 

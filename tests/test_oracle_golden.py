@@ -9,7 +9,7 @@ import pytest
 from helpers import GRAD_RTOL, LOSS_RTOL, golden_names, l2rel, load_golden, maxrel, relerr
 from oracle.oracle import Oracle
 
-OR_KEYS = ("ssim_loss_weight", "photometric_loss_weight", "smoothing_loss_weight", "automask_loss")
+OR_KEYS = ("ssim_loss_weight", "photometric_loss_weight", "smoothing_loss_weight", "automask_loss", "padding_mode")
 
 
 def _oracle(name):

@@ -11,7 +11,7 @@ import torch
 from helpers import GRAD_RTOL, LOSS_RTOL, golden_names, l2rel, load_golden, relerr
 from oracle.torch_port import reference_loss
 
-PORT_KEYS = ("ssim_loss_weight", "photometric_loss_weight", "smoothing_loss_weight", "automask_loss")
+PORT_KEYS = ("ssim_loss_weight", "photometric_loss_weight", "smoothing_loss_weight", "automask_loss", "padding_mode")
 
 
 def _run_port(pred, tgt, hp):
