@@ -31,6 +31,8 @@ struct State {
     unsigned hist3[L3_BINS];
     unsigned count;      // number of ground pixels == compaction cursor
     unsigned nan_flag;   // a ground pixel's height was NaN -> torch.median returns NaN
+    unsigned ticket[3];  // [2]: blocks of pass 3 that are done -- the last one runs the final bin search once for everybody
+    unsigned median;     // bit pattern of the median, written by that block
     unsigned pad[2];
 };
 
@@ -89,7 +91,7 @@ __device__ __forceinline__ void find_bin(const unsigned* __restrict__ hist, unsi
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     unsigned c[PER], s = 0;
 #pragma unroll
-    for (int k = 0; k < PER; k++) { c[k] = hist[tid * PER + k]; s += c[k]; }
+    for (int k = 0; k < PER; k++) { c[k] = __ldcg(hist + tid * PER + k); s += c[k]; }
     unsigned inc = s;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) { unsigned t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
@@ -111,6 +113,19 @@ __device__ __forceinline__ void find_bin(const unsigned* __restrict__ hist, unsi
     __syncthreads();
     bin = s_scan[8]; rank_in_bin = s_scan[9]; found = s_scan[10];
     __syncthreads();
+}
+
+// Takes a ticket for pass `pass` of image state `st`; true (for every thread of the block) in the block that arrives last,
+// after which all histogram updates of the pass are visible to it.
+__device__ __forceinline__ bool last_block(State* st, int pass, unsigned nblocks, unsigned* s_flag)
+{
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) *s_flag = (atomicAdd(&st->ticket[pass], 1u) == nblocks - 1u) ? 1u : 0u;
+    __syncthreads();
+    const bool last = *s_flag != 0u;
+    if (last) __threadfence();
+    return last;
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -235,29 +250,41 @@ __global__ void __launch_bounds__(NT) dgc_refine_kernel(size_t HW, const unsigne
     __shared__ unsigned sScan[16];
     const int tid = threadIdx.x, b = blockIdx.y;
     State* st = states + b;
-    const unsigned count = st->count;
-    if ((size_t)blockIdx.x * NT >= count) return;
-    unsigned bin, rank, found;
-    find_bin<L1_BINS>(st->hist1, (count - 1) >> 1, sScan, bin, rank, found);
-    unsigned prefix = bin, shift = L2_BITS + L3_BITS;
+    const unsigned count = __ldcg(&st->count);
+    if (count == 0) return;
+    // every block repeats the (cheap) bin search of the earlier passes; only the very last search -- which the apply kernel
+    // would otherwise repeat in each of its ~1000 blocks -- is done once, by the last block of pass 3
+    // (measured: a last-block hand-over in every pass costs more in fences than the repeated searches, profiles/r01k)
+    unsigned bin1, rank, found;
+    find_bin<L1_BINS>(st->hist1, (count - 1) >> 1, sScan, bin1, rank, found);
+    unsigned prefix = bin1;
+    constexpr unsigned shift = LEVEL == 2 ? L2_BITS + L3_BITS : L3_BITS;
     if (LEVEL == 3) {
         unsigned bin2;
         find_bin<L2_BINS>(st->hist2, rank, sScan, bin2, rank, found);
-        prefix = (bin << L2_BITS) | bin2;
-        shift = L3_BITS;
+        prefix = (bin1 << L2_BITS) | bin2;
     }
-    for (int i = tid; i < L2_BINS; i += NT) sHist[i] = 0;
-    __syncthreads();
-    const unsigned* kin = keys + (size_t)b * HW;
-    for (size_t i = (size_t)blockIdx.x * NT + tid; i < count; i += (size_t)gridDim.x * NT) {
-        const unsigned k = kin[i];
-        if ((k >> shift) == prefix) atomicAdd(&sHist[(k >> (shift - 10)) & 1023u], 1u);
+    if ((size_t)blockIdx.x * NT < count) {      // block-uniform
+        for (int i = tid; i < L2_BINS; i += NT) sHist[i] = 0;
+        __syncthreads();
+        const unsigned* kin = keys + (size_t)b * HW;
+        for (size_t i = (size_t)blockIdx.x * NT + tid; i < count; i += (size_t)gridDim.x * NT) {
+            const unsigned k = kin[i];
+            if ((k >> shift) == prefix) atomicAdd(&sHist[(k >> (shift - 10)) & 1023u], 1u);
+        }
+        __syncthreads();
+        unsigned* gh = LEVEL == 2 ? st->hist2 : st->hist3;
+        for (int i = tid; i < L2_BINS; i += NT) {
+            const unsigned c = sHist[i];
+            if (c) atomicAdd(&gh[i], c);
+        }
     }
-    __syncthreads();
-    unsigned* gh = LEVEL == 2 ? st->hist2 : st->hist3;
-    for (int i = tid; i < L2_BINS; i += NT) {
-        const unsigned c = sHist[i];
-        if (c) atomicAdd(&gh[i], c);
+    if (LEVEL == 3) {
+        if (last_block(st, 2, gridDim.x, &sScan[12])) {
+            unsigned bin3;
+            find_bin<L3_BINS>(st->hist3, rank, sScan, bin3, rank, found);
+            if (tid == 0) st->median = (prefix << L3_BITS) | bin3;
+        }
     }
 }
 
@@ -271,7 +298,6 @@ __global__ void __launch_bounds__(NT) dgc_apply_kernel(int H, int W, float* __re
                                                        float* __restrict__ points, float* __restrict__ scale_out,
                                                        long long* __restrict__ count_out, const State* __restrict__ states)
 {
-    __shared__ unsigned sScan[16];
     const int tid = threadIdx.x, b = blockIdx.y;
     const size_t HW = (size_t)H * W;
     float scale = 1.0f;
@@ -279,14 +305,7 @@ __global__ void __launch_bounds__(NT) dgc_apply_kernel(int H, int W, float* __re
         const State* st = states + b;
         const unsigned count = st->count;
         scale = __uint_as_float(0x7fc00000u);
-        if (count > 0 && !st->nan_flag) {
-            unsigned b1, b2, b3, rank, found;
-            find_bin<L1_BINS>(st->hist1, (count - 1) >> 1, sScan, b1, rank, found);
-            find_bin<L2_BINS>(st->hist2, rank, sScan, b2, rank, found);
-            find_bin<L3_BINS>(st->hist3, rank, sScan, b3, rank, found);
-            const float med = __uint_as_float((b1 << (L2_BITS + L3_BITS)) | (b2 << L3_BITS) | b3);
-            scale = __fmul_rn(__frcp_rn(med), real_height[b * rh_stride]);
-        }
+        if (count > 0 && !st->nan_flag) scale = __fmul_rn(__frcp_rn(__uint_as_float(st->median)), real_height[b * rh_stride]);
         if (blockIdx.x == 0 && tid == 0) {
             scale_out[b] = scale;
             if (count_out) count_out[b] = (long long)count + (st->nan_flag ? 1 : 0);
