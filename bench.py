@@ -156,6 +156,9 @@ def main():
     ap.add_argument("--backward", default="stash", choices=["stash", "recompute"],
                     help="stash: the forward writes the SSIM-adjoint coefficient texels and the backward consumes them (default, "
                          "fastest); recompute: the backward recomputes the forward from the same tiles (lean memory)")
+    ap.add_argument("--exchange", default="peer", choices=["nccl", "peer"],
+                    help="N>1: how the 3n+3 partial sums cross GPUs -- nccl: all-reduce + finalize kernel; peer: one kernel "
+                         "that pushes them with NVLink P2P stores into symmetric buffers, waits on flags and finalizes")
     ap.add_argument("--e2e-images", default="uint8", choices=["uint8", "float32"],
                     help="dtype of the host images of the e2e leg (uint8 = what the reference's data loader produces)")
     args = ap.parse_args()
@@ -198,7 +201,16 @@ def main():
     from mgnet_b200 import MultiViewPhotometricLoss, _lib, ops
     from mgnet_b200.synthetic import make_inputs
     L = _lib.lib()
-    mod = MultiViewPhotometricLoss(process_group=group, ddp_grad_scale=False, backward=args.backward, **HP)
+    exchange = None
+    if world > 1 and args.exchange == "peer":
+        from mgnet_b200.sharding import PeerExchange
+        try:
+            exchange = PeerExchange(group)
+        except Exception as e:     # no symmetric-memory mapping on this box: the NCCL all-reduce is the same exchange
+            if rank == 0:
+                print("peer exchange unavailable (%s: %s); using the NCCL all-reduce" % (type(e).__name__, e), file=sys.stderr)
+            exchange = None
+    mod = MultiViewPhotometricLoss(process_group=group, exchange=exchange, ddp_grad_scale=False, backward=args.backward, **HP)
 
     # rotating input sets so that no step finds its inputs in L2 (inputs of one set are < L2 for c1/c2)
     in_bytes = B * H * W * (36 + 4 * n + 1)
@@ -392,7 +404,7 @@ def main():
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": desc, "B_per_gpu": B, "H": H, "W": W, "scales": n, "sources": 2, "mask": True,
                        "l2": "rotating %d input sets (%.0f MB) so inputs are never L2-resident" % (nsets, nsets * in_bytes / 1e6),
-                       "parallelism": "batch-sharded x%d, one NCCL all-reduce of %d doubles per step" % (world, 3 * n + 3) if world > 1 else "single GPU",
+                       "parallelism": ("batch-sharded x%d, %s of %d doubles per step" % (world, "one NCCL all-reduce" if exchange is None else "fused peer-memory exchange (NVLink P2P stores + flags, one kernel)", 3 * n + 3)) if world > 1 else "single GPU",
                        "bytes_per_pixel_fwd_bwd": bpp["fwd_bwd"], "backward": args.backward,
                        "stash_bytes_per_pixel": (96 * n if args.backward == "stash" else 0)},
             "roofline": roofline, "cpu_baseline": cpu_base, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,

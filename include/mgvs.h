@@ -156,6 +156,26 @@ int mgvs_project(int B, int H, int W, const float *points, const float *camera, 
                  long long cam_row_stride, const float *pose34, float *coords, void *cuda_stream);
 
 
+/* ---- Sharded batch: peer-memory exchange of the partial sums ----------------------------------------
+ * The only inter-GPU step of the path is the sum of 3n+3 doubles.  Instead of an NCCL all-reduce between mgvs_forward
+ * and mgvs_finalize, ONE single-CTA kernel pushes this rank's sums into every peer's exchange buffer with NVLink P2P
+ * stores, raises a flag there, waits for the other ranks' flags on its own buffer, adds the world's vectors in rank order
+ * (deterministic, bit-identical on every rank) and writes the two losses -- reduction, exchange and finalize in one launch,
+ * no host involvement, no NCCL kernel.  The exchange buffers are symmetric allocations the caller maps into every rank
+ * (torch.distributed._symmetric_memory / cuMem* + fabric or POSIX handles); peer_base[r] is rank r's buffer as seen from
+ * THIS rank.  A buffer holds a step counter, two generations of flags and two generations of world x 32 doubles; it must be
+ * zero-filled once, before the first call on any rank (barrier in between), and every rank must make the same sequence of
+ * calls.  The reference under DDP has no such exchange (each rank normalises by its local mask count). */
+#define MGVS_MAX_RANKS 16
+typedef struct MgvsPeerExchange {
+    int rank, world;                    /* 1 <= world <= MGVS_MAX_RANKS */
+    void *peer_base[MGVS_MAX_RANKS];    /* >= mgvs_exchange_bytes() each, 16-byte aligned; peer_base[rank] is the local one */
+} MgvsPeerExchange;
+size_t mgvs_exchange_bytes(void);
+/*   sums [3n+3] double, in: this rank's partial sums (mgvs_forward); out: the global sums (what mgvs_backward takes)
+ *   losses [2] float out (as mgvs_finalize) */
+int mgvs_exchange_finalize(const MgvsProblem *p, const MgvsPeerExchange *x, double *sums, float *losses, void *cuda_stream);
+
 /* ---- DGC depth rescaling at inference time -------------------------------------------------------
  * Replaces get_depth_prediction(depth_logits, use_dgc_scaling, camera_matrix, real_camera_height, panoptic_seg,
  * road_class_id, depth_filter_class_ids) (mgnet/postprocessing/depth_post_proc.py:11-71) together with its helpers

@@ -74,6 +74,14 @@ class MgvsDgcProblem(ctypes.Structure):
     ]
 
 
+MAX_RANKS = 16
+
+
+class MgvsPeerExchange(ctypes.Structure):
+    """include/mgvs.h: MgvsPeerExchange (peer-memory exchange of the partial sums)."""
+    _fields_ = [("rank", ctypes.c_int), ("world", ctypes.c_int), ("peer_base", ctypes.c_void_p * MAX_RANKS)]
+
+
 def _sources():
     return sorted(os.path.join(_CSRC, f) for f in os.listdir(_CSRC) if f.endswith((".cu", ".cuh"))) + [
         os.path.join(os.path.dirname(_HERE), "include", "mgvs.h")
@@ -163,6 +171,10 @@ def lib():
     L.mgvs_uncertainty_forward.argtypes = [ci, vp, vp, ctypes.POINTER(ctypes.c_float), vp, vp, vp]
     L.mgvs_uncertainty_backward.restype = ci
     L.mgvs_uncertainty_backward.argtypes = [ci, vp, vp, ctypes.POINTER(ctypes.c_float), vp, vp, vp, vp]
+    L.mgvs_exchange_bytes.restype = ctypes.c_size_t
+    L.mgvs_exchange_bytes.argtypes = []
+    L.mgvs_exchange_finalize.restype = ci
+    L.mgvs_exchange_finalize.argtypes = [PP, ctypes.POINTER(MgvsPeerExchange), vp, vp, vp]
     L.mgvs_test_div.restype = ci
     L.mgvs_test_div.argtypes = [vp, vp, vp, ll, vp]
     if L.mgvs_abi_version() != ABI_VERSION:
@@ -176,6 +188,7 @@ EXPORTED_SYMBOLS = (
     "mgvs_finalize", "mgvs_backward", "mgvs_view_synthesis", "mgvs_view_synthesis_ex", "mgvs_reconstruct", "mgvs_project", "mgvs_test_div",
     "mgvs_dgc_workspace_bytes", "mgvs_dgc_rescale", "mgvs_dgc_heights",
     "mgvs_uncertainty_forward", "mgvs_uncertainty_backward",
+    "mgvs_exchange_bytes", "mgvs_exchange_finalize",
 )
 
 

@@ -652,6 +652,72 @@ static int check_launch(const char* what)
 }
 
 
+// ---- sharded batch: push-based all-reduce of the 3n+3 partial sums over peer memory + finalize, one launch -------------
+// Buffer layout (per rank, symmetric): [0] step counter (local use), [64 + 8*(g*MAX_RANKS + r)] flag of rank r in
+// generation g, [1024 + 8*((g*MAX_RANKS + r)*32 + j)] value j of rank r in generation g.  Generation = step & 1: a rank can
+// run at most one step ahead of the slowest one (it needs everybody's flag of step k to leave step k), so two generations
+// never collide.
+constexpr int XCH_FLAGS_OFF = 64, XCH_DATA_OFF = 1024, XCH_VALS = 32;
+constexpr size_t XCH_BYTES = XCH_DATA_OFF + (size_t)2 * MGVS_MAX_RANKS * XCH_VALS * sizeof(double);
+struct PeerPtrs { char* base[MGVS_MAX_RANKS]; };
+
+__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) { asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory"); }
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p)
+{
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ double ld_relaxed_sys_f64(const double* p)
+{
+    double v;
+    asm volatile("ld.relaxed.sys.global.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_relaxed_sys_f64(double* p, double v) { asm volatile("st.relaxed.sys.global.f64 [%0], %1;" ::"l"(p), "d"(v) : "memory"); }
+
+__global__ void __launch_bounds__(256) exchange_finalize_kernel(int n, int rank, int world, PeerPtrs peers, double* __restrict__ sums,
+                                                                float photo_w, float smooth_w, float* __restrict__ losses)
+{
+    __shared__ unsigned long long s_step;
+    __shared__ double s_sums[XCH_VALS];
+    const int tid = threadIdx.x, m = 3 * n + 3;
+    char* mine = peers.base[rank];
+    if (tid == 0) {
+        unsigned long long* ctr = reinterpret_cast<unsigned long long*>(mine);
+        s_step = *ctr + 1ull;
+        *ctr = s_step;
+    }
+    __syncthreads();
+    const unsigned long long step = s_step;
+    const int g = (int)(step & 1ull);
+    // 1. push my vector into every rank's buffer (P2P stores; the local copy goes the same way)
+    for (int idx = tid; idx < world * m; idx += blockDim.x) {
+        const int r = idx / m, j = idx - r * m;
+        double* dst = reinterpret_cast<double*>(peers.base[r] + XCH_DATA_OFF) + ((size_t)(g * MGVS_MAX_RANKS + rank) * XCH_VALS + j);
+        st_relaxed_sys_f64(dst, sums[j]);
+    }
+    __threadfence_system();
+    __syncthreads();
+    // 2. raise my flag everywhere, 3. wait for everybody's flag here
+    if (tid < world) {
+        st_release_sys(reinterpret_cast<unsigned long long*>(peers.base[tid] + XCH_FLAGS_OFF) + (g * MGVS_MAX_RANKS + rank), step);
+        const unsigned long long* f = reinterpret_cast<const unsigned long long*>(mine + XCH_FLAGS_OFF) + (g * MGVS_MAX_RANKS + tid);
+        while (ld_acquire_sys(f) != step) __nanosleep(20);
+    }
+    __syncthreads();
+    // 4. the world's vectors in rank order: deterministic and the same bits on every rank
+    if (tid < m) {
+        double acc = 0.0;
+        for (int r = 0; r < world; r++)
+            acc += ld_relaxed_sys_f64(reinterpret_cast<const double*>(mine + XCH_DATA_OFF) + ((size_t)(g * MGVS_MAX_RANKS + r) * XCH_VALS + tid));
+        s_sums[tid] = acc;
+        sums[tid] = acc;
+    }
+    __syncthreads();
+    if (tid == 0) losses_from_sums_dev(n, s_sums, photo_w, smooth_w, losses);
+}
+
 // ---- uncertainty weighting epilogue (mg_net.py:360-372) --------------------------------------------------------
 struct TauArr { float v[MGVS_MAX_LOSSES]; };
 __global__ void uncertainty_fwd_kernel(int k, const float* __restrict__ raw, const float* __restrict__ log_vars, TauArr tau,
@@ -1050,6 +1116,22 @@ int mgvs_uncertainty_backward(int k, const float* raw, const float* log_vars, co
     if (!g_raw || !g_log_vars) return fail(MGVS_EINVAL, "null argument");
     uncertainty_bwd_kernel<<<1, 32, 0, (cudaStream_t)cuda_stream>>>(k, raw, log_vars, t, g_weighted, g_raw, g_log_vars);
     return check_launch("mgvs_uncertainty_backward");
+}
+
+size_t mgvs_exchange_bytes(void) { return XCH_BYTES; }
+
+int mgvs_exchange_finalize(const MgvsProblem* p, const MgvsPeerExchange* x, double* sums, float* losses, void* cuda_stream)
+{
+    if (!p || !x || !sums || !losses) return fail(MGVS_EINVAL, "null argument");
+    if (p->n < 1 || p->n > MGVS_MAX_SCALES) return fail(MGVS_EINVAL, "bad n");
+    if (x->world < 1 || x->world > MGVS_MAX_RANKS || x->rank < 0 || x->rank >= x->world) return fail(MGVS_EINVAL, "bad rank / world (1..16 ranks)");
+    PeerPtrs pp;
+    for (int r = 0; r < MGVS_MAX_RANKS; r++) {
+        pp.base[r] = r < x->world ? (char*)x->peer_base[r] : nullptr;
+        if (r < x->world && (!pp.base[r] || ((uintptr_t)pp.base[r] & 15))) return fail(MGVS_EINVAL, "peer_base null or not 16-byte aligned");
+    }
+    exchange_finalize_kernel<<<1, 256, 0, (cudaStream_t)cuda_stream>>>(p->n, x->rank, x->world, pp, sums, p->photometric_weight, p->smoothing_weight, losses);
+    return check_launch("mgvs_exchange_finalize");
 }
 
 int mgvs_test_div(const float* a, const float* b, float* out, long long count, void* cuda_stream)

@@ -28,6 +28,7 @@ class MultiViewPhotometricLoss(nn.Module):
         photometric_reduce_op,
         padding_mode,
         process_group=None,
+        exchange=None,
         ddp_grad_scale=False,
         backward="stash",
         fuse_upsample=False,
@@ -41,6 +42,9 @@ class MultiViewPhotometricLoss(nn.Module):
         self.photometric_reduce_op = photometric_reduce_op
         self.padding_mode = padding_mode
         self.process_group = process_group
+        self.exchange = exchange     # sharding.PeerExchange: fused peer-memory exchange + finalize instead of NCCL (see ops.LossConfig)
+        if exchange is not None and process_group is None:
+            raise ValueError("exchange= needs process_group=")
         self.ddp_grad_scale = ddp_grad_scale
         self.fuse_upsample = fuse_upsample   # predictions["depth"] are the head's low-resolution maps; see ops.LossConfig
         self.backward = backward     # "stash" (fast, +48 B/px/scale of scratch) or "recompute" (lean memory), see ops.LossConfig
@@ -68,6 +72,7 @@ class MultiViewPhotometricLoss(nn.Module):
             photometric_reduce_op=self.photometric_reduce_op,
             padding_mode=self.padding_mode,
             process_group=self.process_group,
+            exchange=self.exchange,
             ddp_grad_scale=bool(self.ddp_grad_scale),
             backward=self.backward,
             fuse_upsample=bool(self.fuse_upsample),

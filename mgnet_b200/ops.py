@@ -38,6 +38,8 @@ class LossConfig:
     photometric_reduce_op: str = "min"
     padding_mode: str = "zeros"
     process_group: object = None      # torch.distributed group for the partial-sum all-reduce (None = local)
+    exchange: object = None           # sharding.PeerExchange: the sums cross GPUs inside ONE kernel (NVLink P2P stores +
+                                      # flags + finalize) instead of an NCCL all-reduce + finalize_kernel; needs process_group
     ddp_grad_scale: bool = False      # multiply local grads by world size so DDP's 1/G averaging yields the
                                       # full-batch gradient; only with process_group
     fuse_upsample: bool = False       # predictions["depth"][i] are the depth head's LOW-resolution maps
@@ -181,8 +183,14 @@ class _ViewSynthesisLoss(torch.autograd.Function):
             else:
                 _lib.check(L.mgvs_forward(ctypes.byref(prob), sel.data_ptr(), sums.data_ptr(), stream), "mgvs_forward")
                 launch_counter.n += FWD_LAUNCHES
-                world = allreduce_sums(sums, cfg.process_group)    # the only inter-GPU exchange of the path
-                _lib.check(L.mgvs_finalize(ctypes.byref(prob), sums.data_ptr(), losses.data_ptr(), stream), "mgvs_finalize")
+                if cfg.exchange is not None:
+                    # the only inter-GPU exchange of the path, fused with the finalize: P2P pushes over NVLink in one kernel
+                    world = cfg.exchange.world
+                    _lib.check(L.mgvs_exchange_finalize(ctypes.byref(prob), ctypes.byref(cfg.exchange.struct), sums.data_ptr(),
+                                                        losses.data_ptr(), stream), "mgvs_exchange_finalize")
+                else:
+                    world = allreduce_sums(sums, cfg.process_group)    # same exchange through NCCL
+                    _lib.check(L.mgvs_finalize(ctypes.byref(prob), sums.data_ptr(), losses.data_ptr(), stream), "mgvs_finalize")
                 launch_counter.n += FIN_LAUNCHES
         ctx.cfg = cfg
         ctx.n = n

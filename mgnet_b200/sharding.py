@@ -17,7 +17,7 @@ from __future__ import annotations
 
 import torch
 
-__all__ = ["batch_slice", "allreduce_sums", "losses_from_sums"]
+__all__ = ["batch_slice", "allreduce_sums", "losses_from_sums", "PeerExchange"]
 
 
 def batch_slice(B: int, world_size: int, rank: int) -> slice:
@@ -46,3 +46,35 @@ def losses_from_sums(sums, n: int, photometric_loss_weight: float, smoothing_los
     lp = sum(s[i] / N for i in range(n)) / n
     ls = sum((s[n + 1 + i] / Nx + s[2 * n + 1 + i] / Ny) / (1 << i) for i in range(n)) / n
     return lp * photometric_loss_weight, ls * smoothing_loss_weight
+
+
+class PeerExchange:
+    """Symmetric exchange buffers for ``mgvs_exchange_finalize`` (include/mgvs.h): the partial sums cross GPUs by NVLink
+    P2P stores inside one single-CTA kernel that also finalizes the losses -- no NCCL launch on the step's critical path.
+
+    Pass an instance as ``MultiViewPhotometricLoss(..., process_group=g, exchange=PeerExchange(g))``.  Construction is
+    collective (every rank of the group): it allocates the buffer with torch's symmetric memory, maps the peers'
+    buffers and zero-fills.  Single node only (NVLink / NVSwitch peers); raises if the mapping is unavailable.
+    """
+
+    def __init__(self, group=None, device=None):
+        import torch.distributed as dist
+        import torch.distributed._symmetric_memory as symm
+        from . import _lib
+        self.group = group if group is not None else dist.group.WORLD
+        self.world = dist.get_world_size(self.group)
+        self.rank = dist.get_rank(self.group)
+        if self.world > _lib.MAX_RANKS:
+            raise ValueError("PeerExchange supports up to %d ranks" % _lib.MAX_RANKS)
+        dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        nbytes = int(_lib.lib().mgvs_exchange_bytes())
+        self.buffer = symm.empty(nbytes // 8, dtype=torch.int64, device=dev)
+        self.handle = symm.rendezvous(self.buffer, self.group)
+        self.buffer.zero_()
+        torch.cuda.synchronize(dev)
+        dist.barrier(group=self.group)          # nobody pushes before every buffer is zeroed
+        x = _lib.MgvsPeerExchange()
+        x.rank, x.world = self.rank, self.world
+        for r, ptr in enumerate(self.handle.buffer_ptrs):
+            x.peer_base[r] = int(ptr)
+        self.struct = x
