@@ -43,7 +43,11 @@ WORKLOADS = {
     "c2": ("KITTI Eigen-Zhou loss fwd+bwd, batch 16, 192x640, 2 source frames, 3 scales, automask on", 16, 192, 640, 3),
     "c3": ("Cityscapes-VideoSequence loss fwd+bwd, batch 8, 512x1024, 4 scales at full res", 8, 512, 1024, 4),
     "c4": ("Cityscapes full-res 1024x2048 loss fwd+bwd, batch 8 per GPU (64 over 8 GPUs), 3 scales", 8, 1024, 2048, 3),
+    # BASELINE config[3] verbatim: the SAME 64-image batch sharded over 1/2/4/8 GPUs (strong scaling; 64/N images per GPU,
+    # all 64 on one GPU at N=1: 6.4 GB of inputs + 19 GB of coefficient stash in its 180 GB)
+    "c4s": ("Cityscapes full-res 1024x2048 loss fwd+bwd, batch 64 sharded across the GPUs, 3 scales", 64, 1024, 2048, 3),
 }
+STRONG = {"c4s"}
 HP = dict(ssim_loss_weight=0.85, photometric_loss_weight=1.0, smoothing_loss_weight=1e-3, automask_loss=True,
           photometric_reduce_op="min", padding_mode="zeros")
 L2_BYTES = 126 * 1024 * 1024
@@ -168,6 +172,11 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     desc, B, H, W, n = WORKLOADS[args.workload]
+    strong = args.workload in STRONG
+    if strong:
+        if B % world:
+            raise SystemExit("bench.py: workload %s needs a GPU count dividing %d" % (args.workload, B))
+        B //= world
     bpp = bytes_per_pixel(n)
 
     if args.impl == "reference":
@@ -401,7 +410,7 @@ def main():
         line = {
             "metric": "view-synth loss fwd+bwd Gpixel/s", "value": value, "unit": "Gpixel/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "scaling": "strong" if strong else "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": desc, "B_per_gpu": B, "H": H, "W": W, "scales": n, "sources": 2, "mask": True,
                        "l2": "rotating %d input sets (%.0f MB) so inputs are never L2-resident" % (nsets, nsets * in_bytes / 1e6),
                        "parallelism": ("batch-sharded x%d, %s of %d doubles per step" % (world, "one NCCL all-reduce" if exchange is None else "fused peer-memory exchange (NVLink P2P stores + flags, one kernel)", 3 * n + 3)) if world > 1 else "single GPU",
