@@ -159,6 +159,8 @@ __global__ void __launch_bounds__(NT, MIN_CTAS) fwd_kernel(const FwdParams p, co
     const int u0 = x0 + 4 * tx, v = y0 + ty;     // this thread's 4 outputs: (v, u0..u0+3)
 
     const bool border = (x0 == 0) || (y0 == 0) || (x0 + TW >= W) || (y0 + TH >= H);
+    // NOTE (measured, round 1, profiles/r01k_stagger.txt): delaying the second CTA of every SM by 1-12 us at grid start, so that the
+    // two co-resident CTAs alternate their gather-latency and FP32 stages, changed C2/C4 times by <0.5 %: they de-phase on their own.
     if (p.early_wait) pdl_wait();
     if (USE_TMA) {
         if (tid == 0) {

@@ -2,6 +2,7 @@
 instructions executed, stall samples, shared wavefronts.  Usage: ncu_lines.py rep.ncu-rep [topN]"""
 import csv, subprocess, sys, collections
 rep = sys.argv[1]; top = int(sys.argv[2]) if len(sys.argv) > 2 else 40
+by = 1 if (len(sys.argv) > 3 and sys.argv[3] == "samples") else 0     # sort key: instructions (default) or stall samples
 out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "cuda,sass"], capture_output=True, text=True).stdout
 rows = list(csv.reader(out.splitlines()))
 cur_file = cur_fn = None; hdr = None
@@ -26,6 +27,6 @@ for r in rows:
 for fn in tot:
     print("==== %s: %d warp-instr, %d samples" % (fn, tot[fn][0], tot[fn][1]))
     items = [(k, v) for k, v in agg.items() if k[0] == fn]
-    items.sort(key=lambda kv: -kv[1][0])
+    items.sort(key=lambda kv: -kv[1][by])
     for (f, fl, ln), v in items[:top]:
         print("%5.1f%% inst %5.1f%% smp  smemwf %9d  %s:%d  %s" % (100.0 * v[0] / tot[fn][0], 100.0 * v[1] / max(tot[fn][1], 1), v[2], fl, ln, v[4]))
