@@ -58,8 +58,9 @@ class MultiViewPhotometricLoss(nn.Module):
             raise ValueError("padding_mode must be 'zeros', 'border' or 'reflection', got %r" % (padding_mode,))
         if photometric_reduce_op not in ("min", "mean"):
             raise NotImplementedError("Unknown photometric_reduce_op: {}".format(photometric_reduce_op))
-        if photometric_reduce_op == "mean":
-            raise NotImplementedError("photometric_reduce_op='mean' is not implemented by the fused kernels")
+        # "mean" (loss.py:242-243; only legal with automask off, :106-109) runs the fused path once per source frame with that
+        # frame in both source slots -- min(L, L) = L, index 0 -- and averages the two photometric losses: exact semantics,
+        # twice the cost of "min" (no shipped config selects it)
         if not ssim_loss_weight > 0.0:
             raise NotImplementedError("ssim_loss_weight == 0 (raw 3-channel L1 branch, loss.py:195-196) is not implemented")
 
@@ -89,6 +90,8 @@ class MultiViewPhotometricLoss(nn.Module):
         def img(t):
             return t if t.dtype == torch.uint8 else t.float()
 
+        if self.photometric_reduce_op == "mean":
+            return self._forward_mean(predictions, targets, img)
         with torch.autocast(device_type="cuda", enabled=False):
             lp, ls, sel = view_synthesis_loss(
                 [d.float() for d in inv_depths],
@@ -102,3 +105,25 @@ class MultiViewPhotometricLoss(nn.Module):
             )
         self.last_selection = sel
         return {"loss_photometric": lp, "loss_smoothness": ls}
+
+    def _forward_mean(self, predictions, targets, img):
+        """photometric_reduce_op="mean" (loss.py:242-243): sum_s masked_mean(L_s) / S per scale, averaged over scales -- linear in
+        the per-source losses, so it is the average of two fused "min" evaluations that each see ONE source frame in both slots
+        (identical maps tie, the strict `<` scan keeps index 0, so slot 0 carries the whole gradient).  The smoothness term does
+        not depend on the sources and is taken from the first evaluation."""
+        import dataclasses
+        cfg = dataclasses.replace(self._config(), photometric_reduce_op="min", automask_loss=False)
+        inv = [d.float() for d in predictions["depth"]]
+        poses = predictions["poses"].float()
+        mask = targets["reprojection_mask"] if "reprojection_mask" in targets else None
+        tgt = img(targets["image_orig"])
+        K = targets["camera_matrix"].float()
+        photo, smooth = [], None
+        with torch.autocast(device_type="cuda", enabled=False):
+            for s, key in enumerate(("image_prev_orig", "image_next_orig")):
+                src = img(targets[key])
+                lp, ls, _ = view_synthesis_loss(inv, poses[:, [s, s]], tgt, src, src, K, mask, cfg)
+                photo.append(lp)
+                smooth = ls if smooth is None else smooth
+        self.last_selection = None      # there is no argmin under "mean"
+        return {"loss_photometric": (photo[0] + photo[1]) / 2, "loss_smoothness": smooth}

@@ -34,6 +34,10 @@ CASES = {
     "automask_off": (dict(B=1, H=32, W=64, n=2, seed=5, noise=0.2), {"automask_loss": False}, False),
     "weights_alpha": (dict(B=1, H=36, W=68, n=2, seed=6, noise=0.0, shift_sources=True),
                       {"ssim_loss_weight": 0.5, "photometric_loss_weight": 2.0, "smoothing_loss_weight": 0.05}, False),
+    # photometric_reduce_op="mean" (loss.py:242-243; automask must be off, :106-109).  File name starts with "mean_" so the
+    # selection-mask tests skip it (there is no argmin under "mean")
+    "mean_reduce": (dict(B=2, H=40, W=72, n=2, seed=12, noise=0.0, shift_sources=True),
+                    {"automask_loss": False, "photometric_reduce_op": "mean"}, False),
     # grid_sample padding modes (camera_utils.py:52-54; config.py:116-117): large poses push many samples outside the image
     "pad_border": (dict(B=2, H=40, W=72, n=2, seed=9, noise=0.1, pose_scale=0.06), {"padding_mode": "border"}, True),
     "pad_reflection": (dict(B=2, H=40, W=72, n=2, seed=10, noise=0.0, pose_scale=0.06, shift_sources=True),
@@ -88,6 +92,7 @@ def main(only=None):
             "hp_smoothing_loss_weight": np.float64(hp["smoothing_loss_weight"]),
             "hp_automask_loss": np.bool_(hp["automask_loss"]),
             "hp_padding_mode": np.array(hp["padding_mode"]),
+            "hp_photometric_reduce_op": np.array(hp["photometric_reduce_op"]),
             "loss_photometric": res["loss_photometric"],
             "loss_smoothness": res["loss_smoothness"],
             "grad_poses": res["grad_poses"],

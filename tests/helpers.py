@@ -18,7 +18,7 @@ GRAD_RTOL = 1e-4
 def golden_names():
     """Full-resolution fixtures (the reference's contract).  "fused_*" fixtures hold low-resolution maps."""
     names = sorted(os.path.splitext(os.path.basename(p))[0] for p in glob.glob(os.path.join(GOLDEN, "*.npz")))
-    return [n for n in names if not n.startswith(("fused_", "dgc_"))]
+    return [n for n in names if not n.startswith(("fused_", "dgc_", "mean_"))]
 
 
 def load_golden(name):
@@ -42,7 +42,7 @@ def load_golden(name):
         photometric_loss_weight=float(z["hp_photometric_loss_weight"]),
         smoothing_loss_weight=float(z["hp_smoothing_loss_weight"]),
         automask_loss=bool(z["hp_automask_loss"]),
-        photometric_reduce_op="min",
+        photometric_reduce_op=str(z["hp_photometric_reduce_op"]) if "hp_photometric_reduce_op" in z.files else "min",
         padding_mode=str(z["hp_padding_mode"]) if "hp_padding_mode" in z.files else "zeros",
     )
     ref = {k: z[k] for k in z.files if not k.startswith("in_") and not k.startswith("hp_")}

@@ -62,8 +62,7 @@ def test_module_rejects_unsupported_configs_loudly():
         MultiViewPhotometricLoss(0.85, 1.0, 1e-3, True, "min", mode)
     with pytest.raises(AssertionError):
         MultiViewPhotometricLoss(0.85, 1.0, 1e-3, True, "mean", "zeros")
-    with pytest.raises(NotImplementedError):
-        MultiViewPhotometricLoss(0.85, 1.0, 1e-3, False, "mean", "zeros")
+    MultiViewPhotometricLoss(0.85, 1.0, 1e-3, False, "mean", "zeros")           # legal with automask off (loss.py:106-109); implemented
     with pytest.raises(NotImplementedError):
         MultiViewPhotometricLoss(0.85, 1.0, 1e-3, False, "median", "zeros")
     with pytest.raises(NotImplementedError):

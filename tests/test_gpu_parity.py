@@ -43,7 +43,7 @@ def _run_cuda(pred, tgt, hp, dev, g=(1.0, 1.0), backward="stash"):
     return {
         "loss_photometric": out["loss_photometric"].item(),
         "loss_smoothness": out["loss_smoothness"].item(),
-        "sel": mod.last_selection.cpu().numpy(),
+        "sel": mod.last_selection.cpu().numpy() if mod.last_selection is not None else None,
         "grad_depth": [d.grad.cpu().numpy() for d in p["depth"]],
         "grad_poses": p["poses"].grad.cpu().numpy(),
     }
@@ -218,3 +218,25 @@ def test_stash_and_recompute_backward_agree_at_full_size():
     for x, y in zip(a["grad_depth"], b["grad_depth"]):
         assert l2rel(x, y) <= 5e-5 and maxrel(x, y) <= 5e-5      # each is within 1e-4 of the reference; fp32 summation order differs
     assert l2rel(a["grad_poses"], b["grad_poses"]) <= 1e-5
+
+
+@pytest.mark.parametrize("backward", BACKWARDS)
+def test_mean_reduce_matches_reference_fixture(backward):
+    """photometric_reduce_op="mean" (loss.py:242-243, automask off): fixture from the unmodified reference; also against the
+    oracle composed the same way (one "min" evaluation per source frame, that frame in both slots)."""
+    dev = _dev()
+    from oracle.oracle import Oracle
+    pred, tgt, hp, ref = load_golden("mean_reduce")
+    assert hp["photometric_reduce_op"] == "mean" and not hp["automask_loss"]
+    r = _run_cuda(pred, tgt, hp, dev, backward=backward)
+    assert relerr(r["loss_photometric"], ref["loss_photometric"]) <= LOSS_RTOL
+    assert relerr(r["loss_smoothness"], ref["loss_smoothness"]) <= LOSS_RTOL
+    for i in range(len(pred["depth"])):
+        assert l2rel(r["grad_depth"][i], ref["grad_depth_%d" % i]) <= GRAD_RTOL
+    assert l2rel(r["grad_poses"], ref["grad_poses"]) <= GRAD_RTOL
+    lp = []
+    for s, key in enumerate(("image_prev_orig", "image_next_orig")):
+        t2 = dict(tgt, image_prev_orig=tgt[key], image_next_orig=tgt[key])
+        p2 = {"depth": pred["depth"], "poses": pred["poses"][:, [s, s]].contiguous()}
+        lp.append(float(Oracle(p2, t2, automask_loss=False).forward()["loss_photometric"]))
+    assert relerr(r["loss_photometric"], 0.5 * (lp[0] + lp[1])) <= LOSS_RTOL
