@@ -53,7 +53,8 @@ typedef struct MgvsProblem {
     const unsigned char *mask;                /* targets["reprojection_mask"] [B,1,H,W] bool, or NULL
                                                  (loss.py:147, 237-238) */
     /* MultiViewPhotometricLoss.__init__ arguments (loss.py:87-109, defaults config.py:108-117) */
-    float ssim_weight;          /* float32(ssim_loss_weight) */
+    float ssim_weight;          /* float32(ssim_loss_weight); 0 selects the reference's raw 3-channel L1 branch (loss.py:195-196):
+                                   the min runs over 3 channels per list entry, sel = entry * 3 + channel, no stash */
     float one_minus_ssim_weight;/* float32(1 - ssim_loss_weight) evaluated in double like Python does */
     float photometric_weight;
     float smoothing_weight;

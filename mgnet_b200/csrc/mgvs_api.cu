@@ -610,7 +610,8 @@ static int check_problem(const MgvsProblem* p)
         if (!p->inv_depth[i]) return fail(MGVS_EINVAL, "null inverse-depth pointer");
     if (p->padding_mode < 0 || p->padding_mode > 2) return fail(MGVS_EINVAL, "padding_mode must be 0 (zeros), 1 (border) or 2 (reflection)");
     if (p->reduce_op != 0) return fail(MGVS_EUNSUPPORTED, "photometric_reduce_op: only 'min' is implemented");
-    if (!(p->ssim_weight > 0.f)) return fail(MGVS_EUNSUPPORTED, "ssim_loss_weight must be > 0 (the L1-only branch of loss.py:195-196 is not implemented)");
+    if (!(p->ssim_weight >= 0.f)) return fail(MGVS_EINVAL, "ssim_loss_weight must be >= 0");
+    if (!(p->ssim_weight > 0.f) && lowres_mode(p) != 0) return fail(MGVS_EUNSUPPORTED, "fused upsample with ssim_loss_weight == 0 (it needs the coefficient stash, which the L1-only branch does not have)");
     if (!p->workspace || ((uintptr_t)p->workspace & 255)) return fail(MGVS_EINVAL, "workspace null or not 256-byte aligned");
     if (p->image_dtype != MGVS_IMAGE_F32 && p->image_dtype != MGVS_IMAGE_U8) return fail(MGVS_EINVAL, "image_dtype must be MGVS_IMAGE_F32 or MGVS_IMAGE_U8");
     if (p->workspace_bytes < make_layout(p->B, p->H, p->W, p->n, p->image_dtype).total) return fail(MGVS_EWORKSPACE, "workspace too small");
@@ -822,11 +823,16 @@ size_t mgvs_stash_bytes_ex(int B, int H, int W, int n, int fused_upsample)
 }
 size_t mgvs_stash_bytes(int B, int H, int W, int n) { return mgvs_stash_bytes_ex(B, H, W, n, 0); }
 
-int mgvs_forward_losses(const MgvsProblem* p, unsigned char* sel, double* sums, float* losses, void* cuda_stream)
+int mgvs_forward_losses(const MgvsProblem* p_in, unsigned char* sel, double* sums, float* losses, void* cuda_stream)
 {
-    int rc = check_problem(p);
+    int rc = check_problem(p_in);
     if (rc) return rc;
     if (!sums) return fail(MGVS_EINVAL, "null sums");
+    // ssim_loss_weight == 0 (raw 3-channel L1, loss.py:195-196) has no SSIM adjoint to stash: it always runs the recompute path
+    MgvsProblem pl = *p_in;
+    const bool l1only = !(pl.ssim_weight > 0.f);
+    if (l1only) { pl.stash = nullptr; pl.stash_bytes = 0; }
+    const MgvsProblem* p = &pl;
     cudaStream_t st = (cudaStream_t)cuda_stream;
     Layout L = make_layout(p->B, p->H, p->W, p->n, p->image_dtype);
     char* ws = (char*)p->workspace;
@@ -886,6 +892,9 @@ int mgvs_forward_losses(const MgvsProblem* p, unsigned char* sel, double* sums, 
                                             : (p->stash ? fwd_kernel<false, true> : fwd_kernel<false, false>))
                                  : (use_tma ? (p->stash ? fwd_kernel<true, true, true> : fwd_kernel<true, false, true>)
                                             : (p->stash ? fwd_kernel<false, true, true> : fwd_kernel<false, false, true>));
+        if (l1only)   // ssim_loss_weight == 0: raw 3-channel L1, 12-way min (loss.py:195-196); never with the stash
+            kern = p->padding_mode == 0 ? (use_tma ? fwd_kernel<true, false, false, true> : fwd_kernel<false, false, false, true>)
+                                        : (use_tma ? fwd_kernel<true, false, true, true> : fwd_kernel<false, false, true, true>);
         cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, FWD_SMEM_BYTES);
         launch_pdl(kern, dim3(L.tiles), dim3(NT), FWD_SMEM_BYTES, st, fp, maps);
     }
@@ -908,11 +917,15 @@ int mgvs_finalize(const MgvsProblem* p, const double* sums, float* losses, void*
     return check_launch("mgvs_finalize");
 }
 
-int mgvs_backward(const MgvsProblem* p, const unsigned char* sel, const double* sums, const float* g_losses,
+int mgvs_backward(const MgvsProblem* p_in, const unsigned char* sel, const double* sums, const float* g_losses,
                   float* const* grad_inv, float* grad_poses, void* cuda_stream)
 {
-    int rc = check_problem(p);
+    int rc = check_problem(p_in);
     if (rc) return rc;
+    MgvsProblem pl = *p_in;
+    const bool l1only = !(pl.ssim_weight > 0.f);
+    if (l1only) { pl.stash = nullptr; pl.stash_bytes = 0; }
+    const MgvsProblem* p = &pl;
     if (!sel || !sums || !g_losses || !grad_inv || !grad_poses) return fail(MGVS_EINVAL, "null argument");
     if (lowres_mode(p) && !p->stash) return fail(MGVS_EUNSUPPORTED, "fused upsample: the backward needs the coefficient stash (MgvsProblem.stash, mgvs_stash_bytes_ex(..., 1))");
     cudaStream_t st = (cudaStream_t)cuda_stream;
@@ -1003,6 +1016,9 @@ int mgvs_backward(const MgvsProblem* p, const unsigned char* sel, const double* 
     {
         void (*kern)(BwdParams, BwdMaps) = p->padding_mode == 0 ? (use_tma ? bwd_kernel<true> : bwd_kernel<false>)
                                                                 : (use_tma ? bwd_kernel<true, true> : bwd_kernel<false, true>);
+        if (l1only)
+            kern = p->padding_mode == 0 ? (use_tma ? bwd_kernel<true, false, true> : bwd_kernel<false, false, true>)
+                                        : (use_tma ? bwd_kernel<true, true, true> : bwd_kernel<false, true, true>);
         cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, BWD_SMEM_BYTES);
         kern<<<L.tiles, NT, BWD_SMEM_BYTES, st>>>(bp, maps);
     }

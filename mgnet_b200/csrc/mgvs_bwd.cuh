@@ -102,7 +102,7 @@ __device__ __forceinline__ void box_adjoint4(const float4* __restrict__ mp, cons
             }
 }
 
-template <bool USE_TMA, bool PAD = false>
+template <bool USE_TMA, bool PAD = false, bool L1ONLY = false>
 __global__ void __launch_bounds__(NT, MIN_CTAS) bwd_kernel(const BwdParams p, const __grid_constant__ BwdMaps maps)
 {
     extern __shared__ __align__(128) float smem[];
@@ -171,7 +171,8 @@ __global__ void __launch_bounds__(NT, MIN_CTAS) bwd_kernel(const BwdParams p, co
     const float rw = exact::rcp_refined(wm1), rh = exact::rcp_refined(hm1);
     const float Wp = (float)((double)g_photo * (double)p.photo_w / ((double)p.n * Ntot));
     const float cf_ssim = Wp * p.alpha * (1.0f / 3.0f) * (-0.5f) * (1.0f / 9.0f);   // u/9 of App. B-3
-    const float cf_l1 = Wp * p.oma * (1.0f / 3.0f);
+    // L1ONLY (ssim_loss_weight == 0, loss.py:195-196): raw per-channel |x - y|, no channel mean, no (1 - alpha)
+    const float cf_l1 = L1ONLY ? Wp : Wp * p.oma * (1.0f / 3.0f);
 
     const size_t pimg = (size_t)(H + 2 * PACK_BORDER) * (W + 2 * PACK_BORDER);
     const float4* src0 = p.psrc[0] + (size_t)b * pimg;
@@ -296,6 +297,14 @@ __global__ void __launch_bounds__(NT, MIN_CTAS) bwd_kernel(const BwdParams p, co
         __syncthreads();
 
         float G[S][3][4];
+        if constexpr (L1ONLY) {      // no SSIM term: the box adjoint is zero
+#pragma unroll
+            for (int s = 0; s < S; s++)
+#pragma unroll
+                for (int ch = 0; ch < 3; ch++)
+#pragma unroll
+                    for (int k = 0; k < 4; k++) G[s][ch][k] = 0.f;
+        } else {
 #pragma unroll
         for (int ch = 0; ch < 3; ch++) {
             // ---- stage B: coefficient maps of channel ch ----
@@ -370,6 +379,8 @@ __global__ void __launch_bounds__(NT, MIN_CTAS) bwd_kernel(const BwdParams p, co
             __syncthreads();   // maps free for the next channel
         }
 
+        }   // !L1ONLY
+
         // ---- stage D: per-output chain ----
         float ginv[4];
         // smoothness gradient (App. B-6): d/dinv of sum m*w*|inv_p - inv_q| / (N*c) plus the mean term
@@ -414,14 +425,20 @@ __global__ void __launch_bounds__(NT, MIN_CTAS) bwd_kernel(const BwdParams p, co
                 if (!valid[k]) continue;
                 unsigned code = (selq >> (8 * k)) & 0xffu;
                 bool selme = msk[k] && (p.automask ? (code == 2u * s) : (code == (unsigned)s));
+                unsigned chsel = 3u;         // L1ONLY: the one channel the min picked (code = list entry * 3 + channel)
+                if constexpr (L1ONLY) {
+                    const unsigned entry = code / 3u;
+                    chsel = code - 3u * entry;
+                    selme = msk[k] && (p.automask ? (entry == 2u * s) : (entry == (unsigned)s));
+                }
                 float g0 = G[s][0][k], g1 = G[s][1][k], g2 = G[s][2][k];
                 if (selme) {
                     const float* xq = sX + s * 3 * BWD_CH + (ty + 2) * PITCH + XOFF + 4 * tx + k;
                     const float* yq = sY + (ty + 2) * PITCH + XOFF + 4 * tx + k;
                     float d0 = xq[0] - yq[0], d1 = xq[BWD_CH] - yq[BWD_CH], d2 = xq[2 * BWD_CH] - yq[2 * BWD_CH];
-                    g0 += cf_l1 * (d0 > 0.f ? 1.f : (d0 < 0.f ? -1.f : 0.f));
-                    g1 += cf_l1 * (d1 > 0.f ? 1.f : (d1 < 0.f ? -1.f : 0.f));
-                    g2 += cf_l1 * (d2 > 0.f ? 1.f : (d2 < 0.f ? -1.f : 0.f));
+                    if (!L1ONLY || chsel == 0u) g0 += cf_l1 * (d0 > 0.f ? 1.f : (d0 < 0.f ? -1.f : 0.f));
+                    if (!L1ONLY || chsel == 1u) g1 += cf_l1 * (d1 > 0.f ? 1.f : (d1 < 0.f ? -1.f : 0.f));
+                    if (!L1ONLY || chsel == 2u) g2 += cf_l1 * (d2 > 0.f ? 1.f : (d2 < 0.f ? -1.f : 0.f));
                 }
                 if (g0 == 0.f && g1 == 0.f && g2 == 0.f) continue;
 #ifdef MGVS_SKIP_D

@@ -135,7 +135,7 @@ __device__ __forceinline__ void photometric4(const float* __restrict__ xs, const
         out[k] = __fadd_rn(__fmul_rn(alpha, exact::div3(ssum[k])), __fmul_rn(oma, exact::div3(lsum[k])));
 }
 
-template <bool USE_TMA, bool STASH, bool PAD = false>
+template <bool USE_TMA, bool STASH, bool PAD = false, bool L1ONLY = false>
 __global__ void __launch_bounds__(NT, MIN_CTAS) fwd_kernel(const FwdParams p, const __grid_constant__ FwdMaps maps)
 {
     extern __shared__ __align__(128) float smem[];
@@ -220,6 +220,7 @@ __global__ void __launch_bounds__(NT, MIN_CTAS) fwd_kernel(const FwdParams p, co
     const float* ys_t = sY + ty * PITCH + XOFF + 4 * tx;      // [ch 0][halo row ty][my output 0], 16B aligned
     float* yst_t = sYst + ty * TW + 4 * tx;
     // target statistics for my 4 outputs (shared by all 2+2n photometric evaluations)
+    if constexpr (!L1ONLY) {
 #pragma unroll
     for (int ch = 0; ch < 3; ch++) {
         float sy[4], syy[4];
@@ -249,11 +250,25 @@ __global__ void __launch_bounds__(NT, MIN_CTAS) fwd_kernel(const FwdParams p, co
         *reinterpret_cast<float4*>(yst_t + (ch * 3 + 1) * TH * TW) = make_float4(ms[0], ms[1], ms[2], ms[3]);
         *reinterpret_cast<float4*>(yst_t + (ch * 3 + 2) * TH * TW) = make_float4(sg[0], sg[1], sg[2], sg[3]);
     }
+    }   // !L1ONLY
     // (each thread only reads back its own statistics: no barrier needed)
 
     // identity-reprojection losses (un-warped source vs target), once per tile
     float lid0[4] = {0, 0, 0, 0}, lid1[4] = {0, 0, 0, 0};
-    if (p.automask) {
+    // L1ONLY (ssim_loss_weight == 0): calc_photometric_loss returns the raw 3-channel |x - y| (loss.py:195-196), every list
+    // entry contributes 3 channels to the min and the selection index is entry * 3 + channel
+    float lidc[L1ONLY ? 2 : 1][3][4];
+    if constexpr (L1ONLY) {
+#pragma unroll
+        for (int s = 0; s < 2; s++)
+#pragma unroll
+            for (int ch = 0; ch < 3; ch++)
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    const int o = ch * FWD_CH + (ty + 1) * PITCH + XOFF + 4 * tx + k;
+                    lidc[s][ch][k] = fabsf(__fadd_rn(sX[s * FWD_TILE3_FLOATS + o], -sY[o]));
+                }
+    } else if (p.automask) {
         photometric4<false>(sX + ty * PITCH + XOFF + 4 * tx, ys_t, yst_t, p.alpha, p.oma, lid0, NoEmit());
         photometric4<false>(sX + FWD_TILE3_FLOATS + ty * PITCH + XOFF + 4 * tx, ys_t, yst_t, p.alpha, p.oma, lid1, NoEmit());
     }
@@ -347,7 +362,7 @@ __global__ void __launch_bounds__(NT, MIN_CTAS) fwd_kernel(const FwdParams p, co
                                });
             photometric4<true>(sX + FWD_TILE3_FLOATS + ty * PITCH + XOFF + 4 * tx, ys_t, yst_t, p.alpha, p.oma, lw1,
                                [&](int ch, int k, float a, float bq, float c) { c1[ch][0][k] = a; c1[ch][1][k] = bq; c1[ch][2][k] = c; });
-        } else {
+        } else if constexpr (!L1ONLY) {
             photometric4<false>(sX + ty * PITCH + XOFF + 4 * tx, ys_t, yst_t, p.alpha, p.oma, lw0, NoEmit());
             photometric4<false>(sX + FWD_TILE3_FLOATS + ty * PITCH + XOFF + 4 * tx, ys_t, yst_t, p.alpha, p.oma, lw1, NoEmit());
         }
@@ -355,8 +370,30 @@ __global__ void __launch_bounds__(NT, MIN_CTAS) fwd_kernel(const FwdParams p, co
         unsigned selw = 0;
 #pragma unroll
         for (int k = 0; k < 4; k++) {
-            float best = lw0[k];
+            float best = L1ONLY ? 0.f : lw0[k];
             unsigned bi = 0;
+            if constexpr (L1ONLY) {
+                // strict `<` scan over [warp_prev c0..c2, (id_prev c0..c2,) warp_next c0..c2 (, id_next c0..c2)]
+                float w[2][3];
+#pragma unroll
+                for (int s = 0; s < 2; s++)
+#pragma unroll
+                    for (int ch = 0; ch < 3; ch++) {
+                        const int o = ch * FWD_CH + (ty + 1) * PITCH + XOFF + 4 * tx + k;
+                        w[s][ch] = fabsf(__fadd_rn(sX[s * FWD_TILE3_FLOATS + o], -sY[o]));
+                    }
+                best = w[0][0];
+                unsigned idx = 0;
+#pragma unroll
+                for (int s = 0; s < 2; s++) {
+#pragma unroll
+                    for (int ch = 0; ch < 3; ch++, idx++) if (w[s][ch] < best) { best = w[s][ch]; bi = idx; }
+                    if (p.automask) {
+#pragma unroll
+                        for (int ch = 0; ch < 3; ch++, idx++) if (lidc[s][ch][k] < best) { best = lidc[s][ch][k]; bi = idx; }
+                    }
+                }
+            } else
             if (p.automask) {
                 if (lid0[k] < best) { best = lid0[k]; bi = 1; }
                 if (lw1[k] < best) { best = lw1[k]; bi = 2; }

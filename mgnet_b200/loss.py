@@ -61,8 +61,8 @@ class MultiViewPhotometricLoss(nn.Module):
         # "mean" (loss.py:242-243; only legal with automask off, :106-109) runs the fused path once per source frame with that
         # frame in both source slots -- min(L, L) = L, index 0 -- and averages the two photometric losses: exact semantics,
         # twice the cost of "min" (no shipped config selects it)
-        if not ssim_loss_weight > 0.0:
-            raise NotImplementedError("ssim_loss_weight == 0 (raw 3-channel L1 branch, loss.py:195-196) is not implemented")
+        # ssim_loss_weight == 0 is the reference's raw 3-channel L1 branch (loss.py:195-196): the min then runs over 3 channels
+        # per list entry; the kernels implement it (selection index = entry * 3 + channel), always with the recompute backward
 
     def _config(self) -> LossConfig:
         return LossConfig(

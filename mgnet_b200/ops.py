@@ -164,7 +164,8 @@ class _ViewSynthesisLoss(torch.autograd.Function):
         if cfg.backward not in ("stash", "recompute"):
             raise ValueError("backward must be 'stash' or 'recompute', got %r" % (cfg.backward,))
         # the stash is only worth writing when a backward pass will follow
-        want_stash = cfg.backward == "stash" and any(ctx.needs_input_grad[i] for i in (1,) + tuple(range(7, 7 + n)))
+        # (ssim_loss_weight == 0, the raw-L1 branch, has no SSIM adjoint to stash: the library runs its recompute backward)
+        want_stash = cfg.backward == "stash" and cfg.ssim_loss_weight > 0 and any(ctx.needs_input_grad[i] for i in (1,) + tuple(range(7, 7 + n)))
         with torch.cuda.device(dev):
             ws = torch.empty(int(L.mgvs_workspace_bytes_ex(B, H, W, n, img_dtype)), dtype=torch.uint8, device=dev)
             stash = torch.empty(int(L.mgvs_stash_bytes_ex(B, H, W, n, int(cfg.fuse_upsample))), dtype=torch.uint8, device=dev) if want_stash else None

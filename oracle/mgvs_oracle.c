@@ -307,7 +307,11 @@ int orc_forward(const OrcIn *in, double ssim_w_double, int euler_fma, OrcOut *ou
     const int B = in->B, H = in->H, W = in->W, n = in->n, S = ORC_S;
     const long HW = (long)H * W;
     if (n < 1 || n > ORC_MAX_SCALES || H < 2 || W < 2) return -1;
-    const int nch = in->automask ? 2 * S : S;
+    /* ssim_loss_weight == 0: calc_photometric_loss returns the raw 3-channel |x - y| (loss.py:195-196), so the min of
+       reduce_photometric_loss runs over 3 channels per list entry and sel indexes [entry][channel] */
+    const int l1only = !(ssim_w_double > 0.0);
+    const int cpm = l1only ? 3 : 1;
+    const int nch = (in->automask ? 2 * S : S) * cpm;
     const float alpha_f = (float)ssim_w_double;
     const float oma_f = one_minus_alpha(alpha_f, ssim_w_double);
 
@@ -319,8 +323,8 @@ int orc_forward(const OrcIn *in, double ssim_w_double, int euler_fma, OrcOut *ou
            *Ny = sums + 3 * n + 2;
 
     float *warped = (float *)malloc(sizeof(float) * 3 * HW);
-    float *maps = (float *)malloc(sizeof(float) * 4 * HW);   /* list-ordered loss maps of one scale */
-    float *idm = (float *)malloc(sizeof(float) * S * HW);
+    float *maps = (float *)malloc(sizeof(float) * 12 * HW);  /* list-ordered loss maps of one scale */
+    float *idm = (float *)malloc(sizeof(float) * S * 3 * HW);
     float *wx = (float *)malloc(sizeof(float) * HW), *wy = (float *)malloc(sizeof(float) * HW);
     if (!warped || !maps || !idm || !wx || !wy) return -2;
 
@@ -334,6 +338,11 @@ int orc_forward(const OrcIn *in, double ssim_w_double, int euler_fma, OrcOut *ou
 
         if (in->automask)
             for (int s = 0; s < S; s++) {
+                if (l1only) {
+                    const float *sp = in->source[s] + (long)b * 3 * HW;
+                    for (long p = 0; p < 3 * HW; p++) idm[s * 3 * HW + p] = fabsf(sp[p] - tgt[p]);
+                    continue;
+                }
                 orc_photometric_map(in->source[s] + (long)b * 3 * HW, tgt, H, W, alpha_f, oma_f, idm + s * HW);
                 if (out->identity) memcpy(out->identity + ((long)s * B + b) * HW, idm + s * HW, sizeof(float) * HW);
             }
@@ -370,6 +379,11 @@ int orc_forward(const OrcIn *in, double ssim_w_double, int euler_fma, OrcOut *ou
                 orc_warp(in, b, i, s, K, Kinv, Rt[s], warped, cd);
                 if (out->warped) memcpy(out->warped + (((long)i * S + s) * B + b) * 3 * HW, warped, sizeof(float) * 3 * HW);
                 int slot = in->automask ? 2 * s : s;
+                if (l1only) {
+                    for (long p = 0; p < 3 * HW; p++) maps[slot * 3 * HW + p] = fabsf(warped[p] - tgt[p]);
+                    if (in->automask) memcpy(maps + (2 * s + 1) * 3 * HW, idm + s * 3 * HW, sizeof(float) * 3 * HW);
+                    continue;
+                }
                 orc_photometric_map(warped, tgt, H, W, alpha_f, oma_f, maps + slot * HW);
                 if (out->photo) memcpy(out->photo + (((long)i * S + s) * B + b) * HW, maps + slot * HW, sizeof(float) * HW);
                 if (in->automask) memcpy(maps + (2 * s + 1) * HW, idm + s * HW, sizeof(float) * HW);
@@ -424,6 +438,7 @@ int orc_backward(const OrcIn *in, double ssim_w_double, int euler_fma, const uin
     const long HW = (long)H * W;
     const double alpha = (double)(float)ssim_w_double, oma = (double)(float)(1.0 - ssim_w_double);
     const double N = sums[n], Nx = sums[3 * n + 1], Ny = sums[3 * n + 2];
+    const int l1only = !(ssim_w_double > 0.0);   /* raw 3-channel L1 (loss.py:195-196): sel = entry * 3 + channel */
 
     float *xw[ORC_S];
     double *coef[ORC_S];
@@ -524,6 +539,7 @@ int orc_backward(const OrcIn *in, double ssim_w_double, int euler_fma, const uin
                     if (mk && !mk[p]) continue;
                     int k = sl[p];
                     int s;
+                    if (l1only) continue;   /* no SSIM term */
                     if (in->automask) { if (k & 1) continue; s = k >> 1; } else s = k;
                     for (int ch = 0; ch < 3; ch++) {
                         OrcSsim q;
@@ -584,6 +600,14 @@ int orc_backward(const OrcIn *in, double ssim_w_double, int euler_fma, const uin
                                 int m = mk ? (mk[q] != 0) : 1;
                                 int k = sl[q];
                                 int selq = in->automask ? (k == 2 * s) : (k == s);
+                                if (l1only) {   /* the min picked one (entry, channel): only that channel of that source gets gradient */
+                                    int entry = k / 3;
+                                    selq = (in->automask ? (entry == 2 * s) : (entry == s)) && (k % 3 == ch);
+                                    if (m && selq) {
+                                        float df = xw[s][ch * HW + q] - tgt[ch * HW + q];
+                                        G[ch] += Wp * (double)((df > 0) - (df < 0));
+                                    }
+                                } else
                                 if (m && selq) {
                                     float df = xw[s][ch * HW + q] - tgt[ch * HW + q];
                                     G[ch] += Wp * oma / 3.0 * (double)((df > 0) - (df < 0));

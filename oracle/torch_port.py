@@ -101,6 +101,8 @@ def _ssim(x, y, c1=1e-4, c2=9e-4):
 
 def _photometric(est, tgt, w_ssim):
     l1 = torch.abs(est - tgt)
+    if not w_ssim > 0.0:
+        return l1       # the raw 3-channel map (loss.py:195-196): the min then runs over 3 channels per list entry
     return w_ssim * _ssim(est, tgt).mean(1, True) + (1 - w_ssim) * l1.mean(1, True)
 
 

@@ -38,6 +38,10 @@ CASES = {
     # selection-mask tests skip it (there is no argmin under "mean")
     "mean_reduce": (dict(B=2, H=40, W=72, n=2, seed=12, noise=0.0, shift_sources=True),
                     {"automask_loss": False, "photometric_reduce_op": "mean"}, False),
+    # ssim_loss_weight == 0: raw 3-channel L1, min over 3 channels per list entry (loss.py:195-196)
+    "l1_only": (dict(B=2, H=40, W=72, n=2, seed=13, noise=0.1, shift_sources=True), {"ssim_loss_weight": 0.0}, False),
+    "l1_only_noautomask": (dict(B=1, H=36, W=68, n=2, seed=14, noise=0.0, shift_sources=True),
+                           {"ssim_loss_weight": 0.0, "automask_loss": False}, False),
     # grid_sample padding modes (camera_utils.py:52-54; config.py:116-117): large poses push many samples outside the image
     "pad_border": (dict(B=2, H=40, W=72, n=2, seed=9, noise=0.1, pose_scale=0.06), {"padding_mode": "border"}, True),
     "pad_reflection": (dict(B=2, H=40, W=72, n=2, seed=10, noise=0.0, pose_scale=0.06, shift_sources=True),

@@ -133,7 +133,7 @@ def run_reference(predictions, targets, hp=None, want_grads=True, want_intermedi
                     res["identity_%d" % s] = idm.numpy().copy()
                     for i in range(n):
                         maps[i].append(idm)
-            if hp["ssim_loss_weight"] > 0:
+            if True:   # also for ssim_loss_weight == 0: the maps are 3-channel then and the index is entry * 3 + channel
                 for i in range(n):
                     stack = torch.cat(maps[i], 1)
                     mn, idx = stack.min(1, True)

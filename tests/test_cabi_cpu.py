@@ -65,8 +65,7 @@ def test_module_rejects_unsupported_configs_loudly():
     MultiViewPhotometricLoss(0.85, 1.0, 1e-3, False, "mean", "zeros")           # legal with automask off (loss.py:106-109); implemented
     with pytest.raises(NotImplementedError):
         MultiViewPhotometricLoss(0.85, 1.0, 1e-3, False, "median", "zeros")
-    with pytest.raises(NotImplementedError):
-        MultiViewPhotometricLoss(0.0, 1.0, 1e-3, True, "min", "zeros")
+    MultiViewPhotometricLoss(0.0, 1.0, 1e-3, True, "min", "zeros")              # raw 3-channel L1 branch (loss.py:195-196): implemented
 
 
 def test_cpu_tensors_fail_loudly_no_fallback():
