@@ -191,8 +191,6 @@ __global__ void __launch_bounds__(NT, MIN_CTAS) fwd_kernel(const FwdParams p, co
         __syncthreads();
     }
 
-    const float* K = sCam;
-    const float* Kinv = sCam + 9;
     const float wm1 = (float)(W - 1), hm1 = (float)(H - 1);
     const float rw = exact::rcp_refined(wm1), rh = exact::rcp_refined(hm1);
 
