@@ -44,8 +44,10 @@ g_full = [p.grad.detach().clone() for p in model.parameters()]
 ddp = DDP(model, device_ids=[lr])
 sl = batch_slice(B, world, rank)
 my_t = {k: v[sl].contiguous() for k, v in full_t.items()}
+from mgnet_b200.sharding import PeerExchange
+exchange = PeerExchange(dist.group.WORLD) if os.environ.get("MGVS_EXCHANGE", "peer") == "peer" else None   # fused P2P exchange + finalize
 loss = MultiViewPhotometricLoss(photometric_reduce_op="min", padding_mode="zeros", fuse_upsample=True, process_group=dist.group.WORLD,
-                                ddp_grad_scale=True, **HP)
+                                exchange=exchange, ddp_grad_scale=True, **HP)
 o = run(ddp, loss, my_t, True)
 torch.cuda.synchronize()
 num = sum(float((a.double() - b.grad.double()).pow(2).sum()) for a, b in zip(g_full, model.parameters()))
@@ -60,8 +62,20 @@ K = 10; e0.record()
 for _ in range(K): run(ddp, loss, my_t, True)
 e1.record(); torch.cuda.synchronize()
 ms = torch.tensor([e0.elapsed_time(e1) / K], device=dev); dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+# where the step time goes (events on the compute stream): network forward | loss forward (incl. the exchange) | backward
+ev = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(K)]
+for it in range(K):
+    for p_ in ddp.parameters(): p_.grad = None
+    ev[it][0].record(); pred = ddp(my_t, True)
+    ev[it][1].record(); out = loss(pred, my_t)
+    ev[it][2].record(); (out["loss_photometric"] + out["loss_smoothness"]).backward()
+    ev[it][3].record()
+torch.cuda.synchronize()
+parts = [sum(e[j].elapsed_time(e[j + 1]) for e in ev) / K for j in range(3)]
+if rank == 0:
+    print("DDP_PARTS net_fwd %.3f loss_fwd %.3f backward %.3f ms (%s)" % (parts[0], parts[1], parts[2], "peer" if exchange is not None else "nccl"))
 if rank == 0:
     print("DDP_STEP " + json.dumps({"gpus": world, "B_per_gpu": Bg, "H": H, "W": W, "step_ms": ms.item(), "images_per_s": B / (ms.item() * 1e-3),
-                                   "ddp_grad_vs_full_batch_l2rel": rel, "loss_rel": lrel, "parity": "OK" if ok.item() else "MISMATCH"}))
+                                   "exchange": "peer" if exchange is not None else "nccl", "ddp_grad_vs_full_batch_l2rel": rel, "loss_rel": lrel, "parity": "OK" if ok.item() else "MISMATCH"}))
 dist.destroy_process_group()
 sys.exit(0 if ok.item() else 1)
