@@ -63,7 +63,7 @@ def test_oracle_matches_reference_fixture(name):
 
 @pytest.mark.parametrize("name", DGC_FIXTURES)
 def test_torch_port_matches_reference_fixture(name):
-    """oracle/torch_port.reference_dgc (the comparator scripts/time_dgc.py times) issues the reference's ATen sequence."""
+    """oracle/torch_port.reference_dgc (the comparator tests/tools/time_dgc.py times) issues the reference's ATen sequence."""
     from oracle.torch_port import reference_dgc
     g, use_pan, ids = load_fixture(name)
     out, P, s = reference_dgc(torch.from_numpy(g["in_depth"]).clone(), torch.from_numpy(g["in_camera"]),

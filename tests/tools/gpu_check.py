@@ -1,6 +1,6 @@
 """Verbose GPU parity report (diagnostics; the asserting version is tests/test_gpu_parity.py)."""
 import os, sys, time
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
 import numpy as np, torch
 from helpers import golden_names, load_golden, l2rel, maxrel, relerr

@@ -1,9 +1,9 @@
 """SURVEY 8f-3 measurement: DGC depth rescaling of one image -- the fused sm_100a path (mgnet_b200.postprocessing) against
 (a) the reference's ATen operator sequence on the same GPU (oracle/torch_port.reference_dgc) and (b) the C oracle on the
 host cores.  Also times each kernel through the C ABI with CUDA events and reports the apply kernel against the HBM
-roofline.  Usage: python scripts/time_dgc.py [kitti city]"""
+roofline.  Usage: python tests/tools/time_dgc.py [kitti city]"""
 import ctypes, json, os, sys, time
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 import torch
 from mgnet_b200 import _lib
