@@ -705,7 +705,12 @@ __global__ void __launch_bounds__(256) exchange_finalize_kernel(int n, int rank,
     if (tid < world) {
         st_release_sys(reinterpret_cast<unsigned long long*>(peers.base[tid] + XCH_FLAGS_OFF) + (g * MGVS_MAX_RANKS + rank), step);
         const unsigned long long* f = reinterpret_cast<const unsigned long long*>(mine + XCH_FLAGS_OFF) + (g * MGVS_MAX_RANKS + tid);
-        while (ld_acquire_sys(f) != step) __nanosleep(20);
+        // bounded: a rank that never arrives (unequal call sequences) becomes a launch failure after >= 40 s instead of a hung GPU
+        unsigned long long spins = 0;
+        while (ld_acquire_sys(f) != step) {
+            __nanosleep(20);
+            if (++spins > (1ull << 31)) __trap();
+        }
     }
     __syncthreads();
     // 4. the world's vectors in rank order: deterministic and the same bits on every rank
