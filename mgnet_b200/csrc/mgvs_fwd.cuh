@@ -253,6 +253,7 @@ __global__ void __launch_bounds__(NT, MIN_CTAS) fwd_kernel(const FwdParams p, co
 
     // identity-reprojection losses (un-warped source vs target), once per tile
     float lid0[4] = {0, 0, 0, 0}, lid1[4] = {0, 0, 0, 0};
+    unsigned idnext = 0;     // bit k: the smaller identity loss of output k is id_next (index 3), else id_prev (index 1)
     // L1ONLY (ssim_loss_weight == 0): calc_photometric_loss returns the raw 3-channel |x - y| (loss.py:195-196), every list
     // entry contributes 3 channels to the min and the selection index is entry * 3 + channel
     float lidc[L1ONLY ? 2 : 1][3][4];
@@ -269,6 +270,12 @@ __global__ void __launch_bounds__(NT, MIN_CTAS) fwd_kernel(const FwdParams p, co
     } else if (p.automask) {
         photometric4<false>(sX + ty * PITCH + XOFF + 4 * tx, ys_t, yst_t, p.alpha, p.oma, lid0, NoEmit());
         photometric4<false>(sX + FWD_TILE3_FLOATS + ty * PITCH + XOFF + 4 * tx, ys_t, yst_t, p.alpha, p.oma, lid1, NoEmit());
+        // Only the smaller identity loss can ever win the strict-`<` scan over [warp_prev, id_prev, warp_next, id_next]: keep
+        // min(id_prev, id_next) and which one it is (id_prev on ties: lower index) -- 4 live values instead of 8 through the scale loop.
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            if (lid1[k] < lid0[k]) { lid0[k] = lid1[k]; idnext |= 1u << k; }
+        }
     }
 
     // edge-aware smoothness weights exp(-mean_c |dI|) (depth.py:23-24), premultiplied by mask/validity
@@ -393,9 +400,14 @@ __global__ void __launch_bounds__(NT, MIN_CTAS) fwd_kernel(const FwdParams p, co
                 }
             } else
             if (p.automask) {
-                if (lid0[k] < best) { best = lid0[k]; bi = 1; }
-                if (lw1[k] < best) { best = lw1[k]; bi = 2; }
-                if (lid1[k] < best) { best = lid1[k]; bi = 3; }
+                // same winner as the scan over all four (lid0 now holds min(id_prev, id_next), see above)
+                if ((idnext >> k) & 1u) {
+                    if (lw1[k] < best) { best = lw1[k]; bi = 2; }
+                    if (lid0[k] < best) { best = lid0[k]; bi = 3; }
+                } else {
+                    if (lid0[k] < best) { best = lid0[k]; bi = 1; }
+                    if (lw1[k] < best) { best = lw1[k]; bi = 2; }
+                }
             } else {
                 if (lw1[k] < best) { best = lw1[k]; bi = 1; }
             }
