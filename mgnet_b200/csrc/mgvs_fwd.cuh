@@ -46,7 +46,7 @@ constexpr int FWD_HALO_W = TW + 2;
 constexpr int FWD_TILE3_FLOATS = (3 * FWD_CH + 31) / 32 * 32;      // one 3-channel tile, padded to 128 bytes
 constexpr int FWD_INV_FLOATS = (FWD_CH + 31) / 32 * 32;            // one inverse-depth tile
 constexpr int FWD_SMEM_FLOATS = FWD_TILE3_FLOATS /*Y*/ + S * FWD_TILE3_FLOATS /*X*/ + 2 * FWD_INV_FLOATS /*inv ring*/ +
-                                9 * TH * TW /*Y stats*/ + 8 * 8 /*red*/ + 48 /*cam*/ + 8 /*3 mbarriers*/;
+                                6 * TH * TW /*Y stats: mu_y, sigma_y per channel*/ + 8 * 8 /*red*/ + 48 /*cam*/ + 8 * NT /*smoothness weights*/ + 8 /*3 mbarriers*/;
 constexpr int FWD_SMEM_BYTES = FWD_SMEM_FLOATS * 4;
 
 // Loads a [3,H,W] image tile with 1-pixel halo (reflect-indexed) into smem planes.
@@ -106,11 +106,12 @@ __device__ __forceinline__ void photometric4(const float* __restrict__ xs, const
                 if (dy == 1) l1[k] = fabsf(__fadd_rn(x6[k + 1], -y6[k + 1]));
             }
         }
-        float4 muy = *reinterpret_cast<const float4*>(yst + (ch * 3 + 0) * TH * TW);
-        float4 mys = *reinterpret_cast<const float4*>(yst + (ch * 3 + 1) * TH * TW);
-        float4 sgy = *reinterpret_cast<const float4*>(yst + (ch * 3 + 2) * TH * TW);
-        const float muy4[4] = {muy.x, muy.y, muy.z, muy.w}, mys4[4] = {mys.x, mys.y, mys.z, mys.w},
-                    sgy4[4] = {sgy.x, sgy.y, sgy.z, sgy.w};
+        // mu_y^2 is one rounded multiply away from mu_y: recomputed (same bits) instead of stored -- the 12 KB it used to occupy
+        // keep two resident CTAs inside the 196 KB shared-memory carveout, i.e. 60 KB of L1 for the gathers instead of 28 KB
+        float4 muy = *reinterpret_cast<const float4*>(yst + (ch * 2 + 0) * TH * TW);
+        float4 sgy = *reinterpret_cast<const float4*>(yst + (ch * 2 + 1) * TH * TW);
+        const float muy4[4] = {muy.x, muy.y, muy.z, muy.w}, sgy4[4] = {sgy.x, sgy.y, sgy.z, sgy.w};
+        const float mys4[4] = {__fmul_rn(muy.x, muy.x), __fmul_rn(muy.y, muy.y), __fmul_rn(muy.z, muy.z), __fmul_rn(muy.w, muy.w)};
 #pragma unroll
         for (int k = 0; k < 4; k++) {
             exact::Ssim q;
@@ -142,10 +143,11 @@ __global__ void __launch_bounds__(NT, MIN_CTAS) fwd_kernel(const FwdParams p, co
     float* sY = smem;
     float* sX = sY + FWD_TILE3_FLOATS;          // [S][3][rows][PITCH] (each source tile 128B aligned)
     float* sInv = sX + S * FWD_TILE3_FLOATS;    // [2][rows][PITCH] inverse-depth ring (TMA path)
-    float* sYst = sInv + 2 * FWD_INV_FLOATS;    // [9][TH][TW]
-    float* sRed = sYst + 9 * TH * TW;           // [8 warps][8]
+    float* sYst = sInv + 2 * FWD_INV_FLOATS;    // [6][TH][TW]: (mu_y, sigma_y) per channel
+    float* sRed = sYst + 6 * TH * TW;           // [8 warps][8]
     float* sCam = sRed + 64;                    // 48 floats
-    uint64_t* sBar = reinterpret_cast<uint64_t*>(sCam + 48);   // [0] image tiles, [1],[2] inverse-depth ring
+    float4* sWgt = reinterpret_cast<float4*>(sCam + 48);        // [2][NT]: each thread's masked edge-aware weights (x pairs, y pairs)
+    uint64_t* sBar = reinterpret_cast<uint64_t*>(sCam + 48 + 8 * NT);   // [0] image tiles, [1],[2] inverse-depth ring
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int tile = blockIdx.x;
@@ -244,9 +246,8 @@ __global__ void __launch_bounds__(NT, MIN_CTAS) fwd_kernel(const FwdParams p, co
             ms[k] = __fmul_rn(mu[k], mu[k]);
             sg[k] = __fadd_rn(exact::div9(syy[k]), -ms[k]);
         }
-        *reinterpret_cast<float4*>(yst_t + (ch * 3 + 0) * TH * TW) = make_float4(mu[0], mu[1], mu[2], mu[3]);
-        *reinterpret_cast<float4*>(yst_t + (ch * 3 + 1) * TH * TW) = make_float4(ms[0], ms[1], ms[2], ms[3]);
-        *reinterpret_cast<float4*>(yst_t + (ch * 3 + 2) * TH * TW) = make_float4(sg[0], sg[1], sg[2], sg[3]);
+        *reinterpret_cast<float4*>(yst_t + (ch * 2 + 0) * TH * TW) = make_float4(mu[0], mu[1], mu[2], mu[3]);
+        *reinterpret_cast<float4*>(yst_t + (ch * 2 + 1) * TH * TW) = make_float4(sg[0], sg[1], sg[2], sg[3]);
     }
     }   // !L1ONLY
     // (each thread only reads back its own statistics: no barrier needed)
@@ -300,6 +301,12 @@ __global__ void __launch_bounds__(NT, MIN_CTAS) fwd_kernel(const FwdParams p, co
         cntX += hx ? 1.f : 0.f;
         cntY += hy ? 1.f : 0.f;
     }
+    // parked in shared memory (own slot, no barrier needed) so that they do not occupy 8 registers through the SSIM stages
+    sWgt[tid] = make_float4(wxm[0], wxm[1], wxm[2], wxm[3]);
+    sWgt[NT + tid] = make_float4(wym[0], wym[1], wym[2], wym[3]);
+    // mask counts: reduce now (slots 4..6 of sRed are not used by the per-scale sums), stored after the barrier below
+    cntN = warp_sum(cntN); cntX = warp_sum(cntX); cntY = warp_sum(cntY);
+    if (lane == 0) { sRed[warp * 8 + 4] = cntN; sRed[warp * 8 + 5] = cntX; sRed[warp * 8 + 6] = cntY; }
     if (STASH && v < H && (x0 >> 2) + tx < p.Wg) {
         // the stash backward needs these weights at q, q-1 and q-W: leave them in the stash instead of having it redo the expf
         float* wp = p.wgt + ((size_t)(2 * b) * H + v) * (4 * p.Wg) + u0;
@@ -315,6 +322,12 @@ __global__ void __launch_bounds__(NT, MIN_CTAS) fwd_kernel(const FwdParams p, co
 
     const int nq = 4 * p.n + 3;
     double* my_partials = p.partials + (size_t)tile * nq;
+    if (tid < 3) {
+        double acc = 0.0;
+#pragma unroll
+        for (int w = 0; w < NT / 32; w++) acc += (double)sRed[w * 8 + 4 + tid];
+        my_partials[4 * p.n + tid] = acc;
+    }
     const size_t pimg = (size_t)(H + 2 * PACK_BORDER) * (W + 2 * PACK_BORDER);
     const float4* src0 = p.psrc[0] + (size_t)b * pimg;
     const float4* src1 = p.psrc[1] + (size_t)b * pimg;
@@ -441,11 +454,13 @@ __global__ void __launch_bounds__(NT, MIN_CTAS) fwd_kernel(const FwdParams p, co
             float c4[5];
 #pragma unroll
             for (int k = 0; k < 5; k++) c4[k] = USE_TMA ? si[k] : ((u0 + k < W) ? __ldg(ir + u0 + k) : 0.f);
+            const float4 wx4 = sWgt[tid], wy4 = sWgt[NT + tid];
+            const float wxs[4] = {wx4.x, wx4.y, wx4.z, wx4.w}, wys[4] = {wy4.x, wy4.y, wy4.z, wy4.w};
 #pragma unroll
             for (int k = 0; k < 4; k++) {
                 float below = USE_TMA ? si[PITCH + k] : ((v + 1 < H && u0 + k < W) ? __ldg(ir + W + u0 + k) : 0.f);
-                smx += wxm[k] * fabsf(c4[k] - c4[k + 1]);
-                smy += wym[k] * fabsf(c4[k] - below);
+                smx += wxs[k] * fabsf(c4[k] - c4[k + 1]);
+                smy += wys[k] * fabsf(c4[k] - below);
                 isum += valid[k] ? c4[k] : 0.f;
             }
         }
@@ -458,17 +473,6 @@ __global__ void __launch_bounds__(NT, MIN_CTAS) fwd_kernel(const FwdParams p, co
             for (int w = 0; w < NT / 32; w++) acc += (double)sRed[w * 8 + tid];
             my_partials[tid * p.n + i] = acc;   // [photo | smx | smy | invsum][n]
         }
-    }
-    // mask counts
-    cntN = warp_sum(cntN); cntX = warp_sum(cntX); cntY = warp_sum(cntY);
-    __syncthreads();
-    if (lane == 0) { sRed[warp * 8 + 4] = cntN; sRed[warp * 8 + 5] = cntX; sRed[warp * 8 + 6] = cntY; }
-    __syncthreads();
-    if (tid < 3) {
-        double acc = 0.0;
-#pragma unroll
-        for (int w = 0; w < NT / 32; w++) acc += (double)sRed[w * 8 + 4 + tid];
-        my_partials[4 * p.n + tid] = acc;
     }
 }
 
