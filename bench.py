@@ -216,8 +216,14 @@ def main():
         try:
             exchange = PeerExchange(group)
         except Exception as e:     # no symmetric-memory mapping on this box: the NCCL all-reduce is the same exchange
-            if rank == 0:
-                print("peer exchange unavailable (%s: %s); using the NCCL all-reduce" % (type(e).__name__, e), file=sys.stderr)
+            print("rank %d: peer exchange unavailable (%s: %s)" % (rank, type(e).__name__, e), file=sys.stderr)
+            exchange = None
+        # the choice must be unanimous: a rank spinning on peer flags while another waits in ncclAllReduce would hang
+        okflag = torch.tensor([1 if exchange is not None else 0], device=dev)
+        dist.all_reduce(okflag, op=dist.ReduceOp.MIN, group=group)
+        if int(okflag.item()) == 0:
+            if rank == 0 and exchange is not None:
+                print("peer exchange unavailable on some rank; every rank uses the NCCL all-reduce", file=sys.stderr)
             exchange = None
     mod = MultiViewPhotometricLoss(process_group=group, exchange=exchange, ddp_grad_scale=False, backward=args.backward, **HP)
 
