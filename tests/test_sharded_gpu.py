@@ -19,3 +19,16 @@ def test_sharded_batch_nccl_and_peer_exchange_match_full_batch():
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert "-> OK" in r.stdout and "bit-identical" in r.stdout
+
+
+@pytest.mark.gpu
+def test_full_cityscapes_batch_on_one_gpu():
+    """BASELINE config[3] at its full size on ONE GPU (B=64, 1024x2048: 31 GB with the coefficient stash): size-independent
+    property -- a batch of 8 distinct images repeated 8 times has the loss of the 8, 1/8 of their per-image gradients and
+    repeating selection maps (scripts/check_big_batch.py).  Exercises every >2^31-byte offset of the kernels."""
+    free, _ = torch.cuda.mem_get_info(0)
+    if free < 48 * 2**30:
+        pytest.skip("needs 48 GB of free device memory")
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "scripts", "check_big_batch.py")], capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "-> OK" in r.stdout
