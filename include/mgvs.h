@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define MGVS_ABI_VERSION 5
+#define MGVS_ABI_VERSION 5   /* v2 image_dtype, v3 stash, v4 inv_height/inv_width, v5 padding modes, ssim_weight == 0, DGC, uncertainty, peer exchange */
 #define MGVS_MAX_SCALES 8   /* n: number of inverse-depth maps (reference: 3, mg_net.py:760-764) */
 #define MGVS_NUM_SOURCES 2  /* S: prev, next -- hard-coded in the reference (loss.py:116) */
 
@@ -115,6 +115,7 @@ int mgvs_num_sums(int n);
  * identity automask, per-pixel min, smoothness.  Replaces loss.py:111-149 + geometry/*.
  *   sel  [n,B,H,W] uint8 out (may be NULL): argmin index in the reference's list order
  *        [warp_prev, id_prev, warp_next, id_next] (automask) or [warp_prev, warp_next]; ties -> lowest.
+ *        With ssim_weight == 0 every list entry has 3 channels and the index is entry * 3 + channel (0..11).
  *   sums [3n+3] double out: this rank's partial sums (see above). */
 int mgvs_forward(const MgvsProblem *p, unsigned char *sel, double *sums, void *cuda_stream);
 
