@@ -46,12 +46,14 @@ def test_struct_layout_matches_header():
     from mgnet_b200 import _lib
     with tempfile.TemporaryDirectory() as d:
         src = os.path.join(d, "p.c")
-        open(src, "w").write('#include <stdio.h>\n#include "mgvs.h"\nint main(){printf("%zu %zu\\n", sizeof(MgvsProblem), sizeof(MgvsDgcProblem));return 0;}\n')
+        open(src, "w").write('#include <stdio.h>\n#include "mgvs.h"\nint main(){printf("%zu %zu %zu\\n", sizeof(MgvsProblem), sizeof(MgvsDgcProblem), sizeof(MgvsPeerExchange));return 0;}\n')
         exe = os.path.join(d, "p")
         subprocess.run(["/usr/bin/gcc", "-I", os.path.join(ROOT, "include"), "-o", exe, src], check=True)
-        size, dgc_size = map(int, subprocess.run([exe], capture_output=True, text=True, check=True).stdout.split())
+        size, dgc_size, xch_size = map(int, subprocess.run([exe], capture_output=True, text=True, check=True).stdout.split())
     assert ctypes.sizeof(_lib.MgvsProblem) == size
     assert ctypes.sizeof(_lib.MgvsDgcProblem) == dgc_size
+    assert ctypes.sizeof(_lib.MgvsPeerExchange) == xch_size
+    assert _lib.lib().mgvs_exchange_bytes() == 1024 + 2 * 16 * 32 * 8
 
 
 def test_module_rejects_unsupported_configs_loudly():
