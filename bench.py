@@ -324,6 +324,7 @@ def main():
         pass
     roofline = {"bound": "hbm", "kernel": dominant + "_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                "nominal_peak": 8000.0, "frac_nominal": achieved / 8000.0,      # report against the measured and the nominal 8 TB/s
                 "algorithmic_bytes_per_launch": px_gpu * bpp[dominant], "launch_ms": dom_ms,
                 "fwd_call_ms": fwd_ms, "bwd_call_ms": bwd_ms,
                 "fwd_bwd_frac": px_gpu * bpp["fwd_bwd"] / ((fwd_ms + bwd_ms) * 1e-3) / 1e9 / peak}
