@@ -240,3 +240,33 @@ def test_mean_reduce_matches_reference_fixture(backward):
         p2 = {"depth": pred["depth"], "poses": pred["poses"][:, [s, s]].contiguous()}
         lp.append(float(Oracle(p2, t2, automask_loss=False).forward()["loss_photometric"]))
     assert relerr(r["loss_photometric"], 0.5 * (lp[0] + lp[1])) <= LOSS_RTOL
+
+
+def _random_cases():
+    import test_oracle_random
+    return test_oracle_random.CASES
+
+
+@pytest.mark.parametrize("backward", BACKWARDS)
+@pytest.mark.parametrize("c", _random_cases(), ids=lambda c: "%dx%dx%d_n%d_%s_am%d_a%.2f_p%.2f" % (c["B"], c["H"], c["W"], c["n"], c["pad"], c["automask"], c["ssim"], c["pose_scale"]))
+def test_random_configurations_against_oracle(c, backward):
+    """The randomised configurations of tests/test_oracle_random.py (ragged shapes down to 8 pixels, every padding mode, automask on/off,
+    ssim weights incl. 0, small and large poses) through the CUDA path."""
+    dev = _dev()
+    from mgnet_b200.synthetic import make_inputs
+    from oracle.oracle import Oracle
+    pred, tgt = make_inputs(c["B"], c["H"], c["W"], c["n"], seed=c["seed"], noise=0.0 if c["shift"] else 0.15,
+                            pose_scale=c["pose_scale"], with_mask=c["with_mask"], shift_sources=c["shift"])
+    hp = dict(ssim_loss_weight=c["ssim"], photometric_loss_weight=1.0, smoothing_loss_weight=1e-3, automask_loss=c["automask"],
+              photometric_reduce_op="min", padding_mode=c["pad"])
+    o = Oracle(pred, tgt, **{k: hp[k] for k in OR_KEYS})
+    f = o.forward()
+    g = o.backward(1.0, 1.0)
+    r = _run_cuda(pred, tgt, hp, dev, backward=backward)
+    assert relerr(r["loss_photometric"], f["loss_photometric"]) <= LOSS_RTOL
+    assert relerr(r["loss_smoothness"], f["loss_smoothness"]) <= LOSS_RTOL
+    assert int((r["sel"] != f["sel"]).sum()) == 0
+    for i in range(c["n"]):
+        assert l2rel(r["grad_depth"][i], g["grad_depth"][i]) <= GRAD_RTOL
+    if float(np.abs(g["grad_poses"]).max()) > 0:
+        assert l2rel(r["grad_poses"], g["grad_poses"]) <= GRAD_RTOL
