@@ -200,6 +200,19 @@ def main():
         raise SystemExit("bench.py: no CUDA device; the B200 arm has no CPU fallback (use --impl reference for the CPU port)")
     dev = torch.device("cuda", local_rank)
     torch.cuda.set_device(dev)
+    if world > 1:
+        # keep this rank's host thread and its pinned staging memory on the NUMA node of its GPU (the e2e leg is PCIe-bound)
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            h = pynvml.nvmlDeviceGetHandleByUUID(("GPU-" + str(torch.cuda.get_device_properties(dev).uuid)).encode())
+            words = pynvml.nvmlDeviceGetCpuAffinity(h, (os.cpu_count() + 63) // 64)
+            cpus = {64 * i + b for i, w in enumerate(words) for b in range(64) if (w >> b) & 1}
+            cpus &= os.sched_getaffinity(0)
+            if len(cpus) >= 2:
+                os.sched_setaffinity(0, cpus)
+        except Exception:
+            pass
     import torch.distributed as dist
     group = None
     if world > 1:
