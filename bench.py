@@ -1,24 +1,27 @@
 #!/usr/bin/env python
 """bench.py -- view-synthesis loss fwd+bwd throughput (Gpixel/s) on N B200s of one node.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c2|c3|c4|c1] [--impl reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c4s|c2|c3|c4|c1] [--impl reference]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
         bench.py --gpus N --steps K --warmup W
 
 One "step" = one forward + one backward of the loss over one batch of synthetic inputs (pixels counted
-as B*H*W target pixels).  Prints ONE JSON line on rank 0:
+as B*H*W target pixels).  Default workload = BASELINE.json config[3]: the SAME 64 images of 1024x2048 sharded
+over the N GPUs (64/N images per GPU, all 64 on one GPU at N=1) -- strong scaling.  Prints ONE JSON line on rank 0:
 
   value      whole-job Gpixel/s with inputs resident in HBM (device-timed, max over ranks)
   e2e        the same metric through the public module with HOST (pinned) inputs: H2D copies of every
              input and a D2H read of the two losses inside the timed region
-  roofline   dominant kernel (bwd_kernel): algorithmic bytes per launch / CUDA-event duration, against the
-             measured HBM peak in MEASURED_PEAKS.json
+  roofline   dominant C-ABI call (forward or backward, whichever takes longer; named in roofline.kernel): algorithmic
+             bytes per launch / CUDA-event duration, against the measured HBM peak in MEASURED_PEAKS.json
   cpu_baseline  the ATen-level port of the reference (oracle/torch_port.py) on this box's host cores,
              bounded sample (N=1, rank 0 only)
 
 --impl reference times that CPU port alone (the Python reference cannot travel to the GPU box; the port is
-bit-identical to it, tests/test_torch_port.py) and prints the same line with "impl": "reference".
-Multi-GPU: the batch shards by image; the only exchange is one NCCL all-reduce of 3n+3 doubles (weak scaling).
+bit-identical to it, tests/test_torch_port.py) and prints the same line with "impl": "reference"; for the 1024x2048
+workloads one step of that arm is ONE image ("C4 is timed at B=1 and multiplied by 64").
+Multi-GPU: the batch shards by image; the only exchange is the sum of 3n+3 doubles -- one fused peer-memory kernel
+(NVLink P2P stores + flags + finalize, --exchange peer, default) or one NCCL all-reduce (--exchange nccl).
 """
 from __future__ import annotations
 
@@ -69,7 +72,7 @@ def measured_peak():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+    """nvidia-smi clocks / throttle reasons sampled every 100 ms while the timed region runs."""
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
@@ -83,7 +86,7 @@ class ClockSampler:
             fd, self.path = tempfile.mkstemp(suffix=".csv")
             os.close(fd)
             self.proc = subprocess.Popen(
-                ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "200"],
+                ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
                 stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
         except Exception:
             self.proc = None
@@ -148,12 +151,18 @@ def cpu_reference_run(desc, B_sample, H, W, n, steps, warmup, seed=0):
     return px / dt / 1e9, dt * 1e3, {"cores": cores, "kind": "port", "sample": sample}
 
 
+def cpu_sample_batch(B, H, W):
+    """Images per step of the CPU arm: one image for the 1024x2048 workloads ("C4 is timed at B=1
+    (1024x2048) and multiplied by 64"), else up to 4 of the workload's images."""
+    return 1 if H * W >= 1024 * 2048 else min(B, 4)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=5)
-    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default="c4s", choices=sorted(WORKLOADS))
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -165,6 +174,10 @@ def main():
                          "that pushes them with NVLink P2P stores into symmetric buffers, waits on flags and finalizes")
     ap.add_argument("--e2e-images", default="uint8", choices=["uint8", "float32"],
                     help="dtype of the host images of the e2e leg (uint8 = what the reference's data loader produces)")
+    ap.add_argument("--e2e-depth", default="lowres", choices=["lowres", "full"],
+                    help="what the e2e leg's host hands over as predictions['depth']: lowres = the depth head's low-resolution maps "
+                         "(strides 8/16/32; the module upsamples them in-kernel like the head's F.interpolate and returns low-resolution "
+                         "gradients: fuse_upsample=True, SURVEY 8f-1) -- 0.25 instead of 12 B/px of H2D traffic; full = full-resolution fp32 maps")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
 
@@ -182,13 +195,15 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return 0
-        Bs = min(B, 4)
+        Bs = cpu_sample_batch(B, H, W)
         val, ms, info = cpu_reference_run(desc, Bs, H, W, n, max(args.steps, 1), args.warmup)
         line = {
             "impl": "reference", "metric": "view-synth loss fwd+bwd Gpixel/s", "value": val, "unit": "Gpixel/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": desc, "B_per_step": Bs, "H": H, "W": W, "scales": n, "sources": 2},
+            "higher_is_better": True, "scaling": "strong" if strong else "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": desc, "B_per_step": Bs, "H": H, "W": W, "scales": n, "sources": 2, "mask": True,
+                       "sample": "one step = fwd+bwd of %d image(s) of the workload's shape on all host cores (the CPU arm's throughput does "
+                                 "not depend on how many such steps make up the batch; BASELINE.md section 4)" % Bs},
             "cpu_baseline": dict(info, value=val, unit="Gpixel/s"),
             "e2e": {"value": val, "unit": "Gpixel/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0,
@@ -371,10 +386,17 @@ def main():
             return ({"depth": [v["depth%d" % i] for i in range(n_)], "poses": v["poses"]},
                     {kk: vv for kk, vv in v.items() if not kk.startswith("depth") and kk != "poses"})
 
+        import torch.nn.functional as F
+        lowres = args.e2e_depth == "lowres"
+        strides = ((8, 16, 32) if n <= 3 else (4, 8, 16, 32, 64, 64, 64, 64))[:n]
+        mod_e2e = mod if not lowres else MultiViewPhotometricLoss(process_group=group, exchange=exchange, ddp_grad_scale=False,
+                                                                  backward="stash", fuse_upsample=True, **HP)
         host_arenas, plan, total = [], None, 0
         for pred, tgt in sets_host:
             if args.e2e_images == "uint8":      # what the reference's data loader hands over (mg_net.py:320-335)
                 tgt = quantize_images(tgt)[0]
+            if lowres:                          # what the depth head produces before its own F.interpolate (mg_net.py:799-807)
+                pred = {"depth": [F.avg_pool2d(d, st).contiguous() for d, st in zip(pred["depth"], strides)], "poses": pred["poses"]}
             items, plan, total = layout(pred, tgt)
             ha = torch.empty(total, dtype=torch.uint8).pin_memory()
             hv = views(ha, plan, False)
@@ -410,7 +432,7 @@ def main():
                 upload(k + 1)      # prefetch the next step's inputs while this step computes
             for x in sl.pd["depth"] + [sl.pd["poses"]]:
                 x.grad = None
-            out = mod(sl.pd, sl.td)
+            out = mod_e2e(sl.pd, sl.td)
             (out["loss_photometric"] + out["loss_smoothness"]).backward()
             out_host.copy_(torch.stack([out["loss_photometric"].detach(), out["loss_smoothness"].detach()]), non_blocking=True)
             sl.free.record(cur)
@@ -435,16 +457,20 @@ def main():
         ms_e = float(te.item()) / args.steps
         e2e = {"value": px_step / (ms_e * 1e-3) / 1e9, "unit": "Gpixel/s", "h2d_bytes_per_step": int(h2d),
                "d2h_bytes_per_step": 8, "ms_per_step": ms_e, "wall_ms_per_step": wall_ms / args.steps,
-               "images": args.e2e_images,
-               "note": "pinned host inputs (images as %s, inverse depth fp32) in one arena -> ONE H2D copy per step, overlapped with the compute of the previous step on a copy stream" % (
-                   "the data loader's uint8, converted in-kernel like the reference's x.float()/255" if args.e2e_images == "uint8" else "float32")}
+               "images": args.e2e_images, "depth": args.e2e_depth,
+               "h2d_gbs_per_rank": h2d / (ms_e * 1e-3) / 1e9,
+               "note": "pinned host inputs (images as %s; inverse depth as %s) in one arena -> ONE H2D copy per step, overlapped with the compute of the previous step on a copy stream" % (
+                   "the data loader's uint8, converted in-kernel like the reference's x.float()/255" if args.e2e_images == "uint8" else "float32",
+                   "the depth head's low-resolution fp32 maps (strides %s), upsampled in-kernel bit-identically to its F.interpolate(bilinear, align_corners=True); "
+                   "gradients return at low resolution (fuse_upsample=True)" % (list(strides),) if lowres else "full-resolution fp32 maps")}
 
     clocks = sampler.stop() if rank == 0 else None
 
     cpu_base = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        Bs = min(B, 4)
-        v, ms, info = cpu_reference_run(desc, Bs, H, W, n, 3, 1)
+        Bs = cpu_sample_batch(B, H, W)
+        # ~10-20 s of CPU work: ~0.6 s per 1024x2048 image, ~0.15 s per 4 images of 192x640 on 16 threads
+        v, ms, info = cpu_reference_run(desc, Bs, H, W, n, 16 if H * W >= 1024 * 2048 else (6 if H * W >= 512 * 1024 else 40), 1)
         cpu_base = dict(info, value=v, unit="Gpixel/s", ms_per_sample_step=ms)
 
     if rank == 0:

@@ -23,7 +23,8 @@
 extern "C" {
 #endif
 
-#define MGVS_ABI_VERSION 5   /* v2 image_dtype, v3 stash, v4 inv_height/inv_width, v5 padding modes, ssim_weight == 0, DGC, uncertainty, peer exchange */
+#define MGVS_ABI_VERSION 6   /* v2 image_dtype, v3 stash, v4 inv_height/inv_width, v5 padding modes, ssim_weight == 0, DGC, uncertainty, peer exchange,
+                                v6 pose_mats, camera_lift of mgvs_view_synthesis_ex, differentiable geometry ops, pose tail, exchange status */
 #define MGVS_MAX_SCALES 8   /* n: number of inverse-depth maps (reference: 3, mg_net.py:760-764) */
 #define MGVS_NUM_SOURCES 2  /* S: prev, next -- hard-coded in the reference (loss.py:116) */
 
@@ -32,7 +33,7 @@ enum { MGVS_IMAGE_F32 = 0, MGVS_IMAGE_U8 = 1 };
 enum {
     MGVS_OK = 0,
     MGVS_EINVAL = -1,       /* bad dims / null pointer / misaligned pointer */
-    MGVS_EUNSUPPORTED = -2, /* legal in the reference but not implemented (padding_mode != zeros, ...) */
+    MGVS_EUNSUPPORTED = -2, /* legal in the reference but not implemented by this build (e.g. fused upsample with W % 4 != 0) */
     MGVS_EWORKSPACE = -3,   /* workspace too small */
     MGVS_ECUDA = -4         /* launch failure */
 };
@@ -49,7 +50,8 @@ typedef struct MgvsProblem {
                                                  only [:, :3, :3] is read       (loss.py:122-123) */
     long long cam_batch_stride, cam_row_stride;
     const float *poses;                       /* predictions["poses"]        [B,S,6] (tx,ty,tz,rx,ry,rz)
-                                                 target->source, Euler        (loss.py:117-119) */
+                                                 target->source, Euler        (loss.py:117-119); may be NULL
+                                                 when pose_mats is given */
     const unsigned char *mask;                /* targets["reprojection_mask"] [B,1,H,W] bool, or NULL
                                                  (loss.py:147, 237-238) */
     /* MultiViewPhotometricLoss.__init__ arguments (loss.py:87-109, defaults config.py:108-117) */
@@ -59,7 +61,8 @@ typedef struct MgvsProblem {
     float photometric_weight;
     float smoothing_weight;
     int automask;               /* automask_loss */
-    int reduce_op;              /* 0 = "min" (the only one implemented) */
+    int reduce_op;              /* 0 = "min".  "mean" (loss.py:242-243) is composed by the caller from two "min" evaluations that each see one
+                                   source frame in both slots (mgnet_b200/loss.py _forward_mean); any other value is refused */
     int padding_mode;           /* grid_sample padding_mode (camera_utils.py:52-54): 0 = "zeros", 1 = "border", 2 = "reflection" */
     void *workspace;            /* >= mgvs_workspace_bytes(B,H,W,n) bytes, 256-byte aligned; must stay
                                    untouched between mgvs_forward and the matching mgvs_backward */
@@ -86,6 +89,12 @@ typedef struct MgvsProblem {
                                    upsample is applied in fixed order: deterministic, unlike ATen's atomics on CUDA).  All
                                    maps must be low resolution or none; needs the stash (mgvs_stash_bytes_ex(..., 1)),
                                    W % 4 == 0 and 16-byte aligned image tensors. */
+    const float *pose_mats;     /* optional [B,S,3,4] row-major (R|t): rows 0..2 of the 4x4 the reference builds with
+                                   Pose.from_vec -> pose_vec2mat (pose.py:41-47, pose_utils.py:41-51).  Non-NULL replaces the in-kernel
+                                   Euler evaluation of `poses`: a caller that forms R with torch gets the reference's own rotation bits
+                                   (torch-CPU sin/cos are MKL-VML values, 1 ulp off the correctly rounded ones the kernel uses for ~5 %
+                                   of arguments), so the selection mask is bit-exact for ANY angles.  mgvs_backward then writes
+                                   grad_poses as [B,S,3,4] = dL/d(R|t) (no Euler chain; autograd of the caller's pose_vec2mat does it). */
 } MgvsProblem;
 
 int mgvs_abi_version(void);
@@ -132,20 +141,24 @@ int mgvs_finalize(const MgvsProblem *p, const double *sums, float *losses, void 
  *   sel, sums   as produced by mgvs_forward (sums after the all-reduce if sharded)
  *   g_losses    [2] float, upstream gradients of (loss_photometric, loss_smoothness)
  *   grad_inv[i] [B,1,H,W] float out, fully overwritten
- *   grad_poses  [B,S,6] float out, fully overwritten; deterministic (no float atomics) */
+ *   grad_poses  [B,S,6] float out ([B,S,3,4] when p->pose_mats is given), fully overwritten; deterministic (no float atomics) */
 int mgvs_backward(const MgvsProblem *p, const unsigned char *sel, const double *sums, const float *g_losses,
                   float *const *grad_inv, float *grad_poses, void *cuda_stream);
 
-/* ---- mgnet.geometry primitives (forward only) ---------------------------------------------------- */
+/* ---- mgnet.geometry primitives (forward only: the Python mirror raises when an input requires grad -- gradients of the
+ * training path flow through mgvs_backward) ------------------------------------------------------------------------- */
 
 /* view_synthesis (camera_utils.py:24-54): warped[B,3,H,W] = grid_sample(ref_image, project(reconstruct(depth))).
  * depth is METRIC depth (already 1/inv); pose34 is [B,3,4] (R|t) of ref_cam.Tcw, K as in MgvsProblem. */
 int mgvs_view_synthesis(int B, int H, int W, const float *ref_image, const float *depth, const float *camera,
                         long long cam_batch_stride, long long cam_row_stride, const float *pose34,
                         float *warped, float *coords /* [B,H,W,2] or NULL */, void *cuda_stream);
-/* Same with grid_sample's padding_mode (camera_utils.py:52-54): 0 zeros, 1 border, 2 reflection. */
+/* Same with grid_sample's padding_mode (camera_utils.py:52-54): 0 zeros, 1 border, 2 reflection, and with the two cameras
+ * of the reference's signature kept apart: `camera` = ref_cam.K projects (camera_utils.py:50), `camera_lift` = cam.K
+ * back-projects (camera_utils.py:48; NULL = the same matrix).  They differ when one of the cameras was Camera.scaled(). */
 int mgvs_view_synthesis_ex(int B, int H, int W, const float *ref_image, const float *depth, const float *camera,
-                           long long cam_batch_stride, long long cam_row_stride, const float *pose34, int padding_mode,
+                           long long cam_batch_stride, long long cam_row_stride, const float *camera_lift,
+                           long long lift_batch_stride, long long lift_row_stride, const float *pose34, int padding_mode,
                            float *warped, float *coords /* [B,H,W,2] or NULL */, void *cuda_stream);
 
 /* Camera.reconstruct(depth, frame="c") (camera.py:107-136): points[B,3,H,W] = (K^-1 grid) * depth. */

@@ -15,7 +15,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _CSRC = os.path.join(_HERE, "csrc")
 LIB_PATH = os.environ.get("MGVS_LIB_PATH") or os.path.join(_HERE, "libmgvs.so")   # override: kernel-variant experiments only
 MAX_SCALES = 8
-ABI_VERSION = 5
+ABI_VERSION = 6
 IMAGE_F32, IMAGE_U8 = 0, 1
 NUM_SOURCES = 2
 
@@ -42,6 +42,7 @@ class MgvsProblem(ctypes.Structure):
         ("image_dtype", ctypes.c_int),
         ("stash", ctypes.c_void_p), ("stash_bytes", ctypes.c_size_t),
         ("inv_height", ctypes.c_int * MAX_SCALES), ("inv_width", ctypes.c_int * MAX_SCALES),
+        ("pose_mats", ctypes.c_void_p),
     ]
 
 
@@ -155,7 +156,7 @@ def lib():
     L.mgvs_view_synthesis.restype = ci
     L.mgvs_view_synthesis.argtypes = [ci, ci, ci, vp, vp, vp, ll, ll, vp, vp, vp, vp]
     L.mgvs_view_synthesis_ex.restype = ci
-    L.mgvs_view_synthesis_ex.argtypes = [ci, ci, ci, vp, vp, vp, ll, ll, vp, ci, vp, vp, vp]
+    L.mgvs_view_synthesis_ex.argtypes = [ci, ci, ci, vp, vp, vp, ll, ll, vp, ll, ll, vp, ci, vp, vp, vp]
     L.mgvs_reconstruct.restype = ci
     L.mgvs_reconstruct.argtypes = [ci, ci, ci, vp, vp, ll, ll, vp, vp]
     L.mgvs_project.restype = ci

@@ -144,7 +144,7 @@ static Layout make_layout(int B, int H, int W, int n, int image_dtype = 0)
 // sin/cos are the correctly rounded fp32 values (fp64 evaluation); the two tiny bmm's of euler2mat
 // round like ATen's small-matrix path: acc = 0; acc += a*b with separately rounded mul and add.
 __device__ __forceinline__ void prep_one(int b, const float* __restrict__ camera, long long cbs, long long crs,
-                                         const float* __restrict__ poses, Cam* __restrict__ cams)
+                                         const float* __restrict__ poses, const float* __restrict__ pose_mats, Cam* __restrict__ cams)
 {
     Cam c;
     for (int r = 0; r < 3; r++)
@@ -156,6 +156,10 @@ __device__ __forceinline__ void prep_one(int b, const float* __restrict__ camera
     c.Kinv[2] = __fdiv_rn(__fmul_rn(-1.0f, cx), fx);
     c.Kinv[5] = __fdiv_rn(__fmul_rn(-1.0f, cy), fy);
     for (int s = 0; s < S; s++) {
+        if (pose_mats != nullptr) {      // the caller's own (R|t), MgvsProblem.pose_mats: copied bit for bit
+            for (int k = 0; k < 12; k++) c.Rt[s][k] = pose_mats[((size_t)b * S + s) * 12 + k];
+            continue;
+        }
         const float* v = poses + ((size_t)b * S + s) * 6;
         float cxr = (float)cos((double)v[3]), sxr = (float)sin((double)v[3]);
         float cyr = (float)cos((double)v[4]), syr = (float)sin((double)v[4]);
@@ -195,11 +199,11 @@ __device__ __forceinline__ void prep_one(int b, const float* __restrict__ camera
 __global__ void __launch_bounds__(256) pack_sources_kernel(int B, int H, int W, const float* __restrict__ s0,
                                                            const float* __restrict__ s1, float4* __restrict__ o0, float4* __restrict__ o1,
                                                            const float* __restrict__ camera, long long cbs, long long crs,
-                                                           const float* __restrict__ poses, Cam* __restrict__ cams)
+                                                           const float* __restrict__ poses, const float* __restrict__ pose_mats, Cam* __restrict__ cams)
 {
     pdl_trigger();     // fwd_kernel may start its prologue (it waits before reading what this kernel writes)
     if (blockIdx.x == gridDim.x - 1) {
-        for (int b = threadIdx.x; b < B; b += blockDim.x) prep_one(b, camera, cbs, crs, poses, cams);
+        for (int b = threadIdx.x; b < B; b += blockDim.x) prep_one(b, camera, cbs, crs, poses, pose_mats, cams);
         return;
     }
     const int Wp = W + 2 * PACK_BORDER, Hp = H + 2 * PACK_BORDER;
@@ -233,11 +237,11 @@ __global__ void __launch_bounds__(256) pack_u8_kernel(int B, int H, int W, const
                                                       float* __restrict__ ftg, float* __restrict__ f0, float* __restrict__ f1,
                                                       float4* __restrict__ o0, float4* __restrict__ o1,
                                                       const float* __restrict__ camera, long long cbs, long long crs,
-                                                      const float* __restrict__ poses, Cam* __restrict__ cams)
+                                                      const float* __restrict__ poses, const float* __restrict__ pose_mats, Cam* __restrict__ cams)
 {
     pdl_trigger();
     if (blockIdx.x == gridDim.x - 1) {
-        for (int b = threadIdx.x; b < B; b += blockDim.x) prep_one(b, camera, cbs, crs, poses, cams);
+        for (int b = threadIdx.x; b < B; b += blockDim.x) prep_one(b, camera, cbs, crs, poses, pose_mats, cams);
         return;
     }
     const int Wp = W + 2 * PACK_BORDER, Hp = H + 2 * PACK_BORDER;
@@ -383,7 +387,8 @@ __global__ void finalize_kernel(int n, const double* __restrict__ sums, float ph
 // Pose gradient: fixed-order sum of the per-tile partials of dL/d(R|t), then the Euler chain through
 // R = Rx Ry Rz (pose_utils.py:14-38); vec = (tx,ty,tz,rx,ry,rz).  One CTA per (image, source).
 __global__ void __launch_bounds__(128) pose_reduce_kernel(int tiles_per_image, const float* __restrict__ pose_partials,
-                                                          const float* __restrict__ poses, float* __restrict__ grad_poses)
+                                                          const float* __restrict__ poses /* null: matrix input, grad = dL/d(R|t) [.,3,4] */,
+                                                          float* __restrict__ grad_poses)
 {
     __shared__ double sh[12][128];
     __shared__ double g[12];
@@ -403,6 +408,10 @@ __global__ void __launch_bounds__(128) pose_reduce_kernel(int tiles_per_image, c
     }
     if (tid < 12) g[tid] = sh[tid][0];
     __syncthreads();
+    if (poses == nullptr) {      // MgvsProblem.pose_mats: the 12 sums are the gradient
+        if (tid < 12) grad_poses[(size_t)bs * 12 + tid] = (float)g[tid];
+        return;
+    }
     if (tid != 0) return;
     const float* v = poses + (size_t)bs * 6;
     double cx = cos((double)v[3]), sx = sin((double)v[3]);
@@ -444,8 +453,11 @@ __global__ void test_div_kernel(const float* a, const float* b, float* out, long
 }
 
 // ---- standalone geometry primitives ------------------------------------------------------------
+// camera: ref_cam.K (projection, camera_utils.py:50); lift: cam.K (back-projection, camera_utils.py:48) -- the reference lifts
+// with the target camera and projects with the reference camera, which differ for Camera.scaled users
 __global__ void view_synthesis_kernel(int B, int H, int W, const float* __restrict__ ref, const float* __restrict__ depth,
                                       const float* __restrict__ camera, long long cbs, long long crs,
+                                      const float* __restrict__ lift, long long lbs, long long lrs,
                                       const float* __restrict__ pose34, float* __restrict__ warped, float* __restrict__ coords, int pad)
 {
     const int HW = H * W;
@@ -454,12 +466,14 @@ __global__ void view_synthesis_kernel(int B, int H, int W, const float* __restri
     int b = (int)(idx / HW), pix = (int)(idx - (long long)b * HW), v = pix / W, u = pix - v * W;
     float K[9], Kinv[9], Rt[12];
     for (int r = 0; r < 3; r++)
-        for (int k = 0; k < 3; k++) K[r * 3 + k] = camera[b * cbs + r * crs + k];
-    for (int k = 0; k < 9; k++) Kinv[k] = K[k];
-    Kinv[0] = __fdiv_rn(1.0f, K[0]);
-    Kinv[4] = __fdiv_rn(1.0f, K[4]);
-    Kinv[2] = __fdiv_rn(__fmul_rn(-1.0f, K[2]), K[0]);
-    Kinv[5] = __fdiv_rn(__fmul_rn(-1.0f, K[5]), K[4]);
+        for (int k = 0; k < 3; k++) { K[r * 3 + k] = camera[b * cbs + r * crs + k]; Kinv[r * 3 + k] = lift[b * lbs + r * lrs + k]; }
+    {   // Camera.Kinv of the lifting camera (camera.py:72-81)
+        const float fx = Kinv[0], fy = Kinv[4], cx = Kinv[2], cy = Kinv[5];
+        Kinv[0] = __fdiv_rn(1.0f, fx);
+        Kinv[4] = __fdiv_rn(1.0f, fy);
+        Kinv[2] = __fdiv_rn(__fmul_rn(-1.0f, cx), fx);
+        Kinv[5] = __fdiv_rn(__fmul_rn(-1.0f, cy), fy);
+    }
     for (int k = 0; k < 12; k++) Rt[k] = pose34[(size_t)b * 12 + k];
     float r[3], Xc[3];
     exact::ray(Kinv, u, v, r);
@@ -605,11 +619,11 @@ static int check_problem(const MgvsProblem* p)
     if (!p) return fail(MGVS_EINVAL, "null problem");
     if (p->B < 1 || p->H < 3 || p->W < 3 || p->n < 1 || p->n > MGVS_MAX_SCALES) return fail(MGVS_EINVAL, "bad dims (need B>=1, H,W>=3, 1<=n<=8)");
     if ((long long)p->H * p->W * 3 >= (1ll << 31)) return fail(MGVS_EINVAL, "image plane too large for 32-bit indexing");
-    if (!p->target || !p->source[0] || !p->source[1] || !p->camera || !p->poses) return fail(MGVS_EINVAL, "null input pointer");
+    if (!p->target || !p->source[0] || !p->source[1] || !p->camera || (!p->poses && !p->pose_mats)) return fail(MGVS_EINVAL, "null input pointer");
     for (int i = 0; i < p->n; i++)
         if (!p->inv_depth[i]) return fail(MGVS_EINVAL, "null inverse-depth pointer");
     if (p->padding_mode < 0 || p->padding_mode > 2) return fail(MGVS_EINVAL, "padding_mode must be 0 (zeros), 1 (border) or 2 (reflection)");
-    if (p->reduce_op != 0) return fail(MGVS_EUNSUPPORTED, "photometric_reduce_op: only 'min' is implemented");
+    if (p->reduce_op != 0) return fail(MGVS_EUNSUPPORTED, "photometric_reduce_op: the kernels implement 'min'; 'mean' is composed from two 'min' evaluations by the caller (mgnet_b200/loss.py)");
     if (!(p->ssim_weight >= 0.f)) return fail(MGVS_EINVAL, "ssim_loss_weight must be >= 0");
     if (!(p->ssim_weight > 0.f) && lowres_mode(p) != 0) return fail(MGVS_EUNSUPPORTED, "fused upsample with ssim_loss_weight == 0 (it needs the coefficient stash, which the L1-only branch does not have)");
     if (!p->workspace || ((uintptr_t)p->workspace & 255)) return fail(MGVS_EINVAL, "workspace null or not 256-byte aligned");
@@ -862,10 +876,10 @@ int mgvs_forward_losses(const MgvsProblem* p_in, unsigned char* sel, double* sum
             pack_u8_kernel<<<blocks + 1, 256, 0, st>>>(p->B, p->H, p->W, (const unsigned char*)p->target, (const unsigned char*)p->source[0],
                                                        (const unsigned char*)p->source[1], (float*)(ws + L.planar[0]), (float*)(ws + L.planar[1]),
                                                        (float*)(ws + L.planar[2]), (float4*)(ws + L.packed[0]), (float4*)(ws + L.packed[1]),
-                                                       p->camera, p->cam_batch_stride, p->cam_row_stride, p->poses, cams);
+                                                       p->camera, p->cam_batch_stride, p->cam_row_stride, p->poses, p->pose_mats, cams);
         else
             pack_sources_kernel<<<blocks + 1, 256, 0, st>>>(p->B, p->H, p->W, src_f[0], src_f[1], (float4*)(ws + L.packed[0]),
-                                                            (float4*)(ws + L.packed[1]), p->camera, p->cam_batch_stride, p->cam_row_stride, p->poses, cams);
+                                                            (float4*)(ws + L.packed[1]), p->camera, p->cam_batch_stride, p->cam_row_stride, p->poses, p->pose_mats, cams);
     }
     fp.partials = (double*)(ws + L.partials);
     fp.alpha = p->ssim_weight; fp.oma = p->one_minus_ssim_weight;
@@ -985,7 +999,7 @@ int mgvs_backward(const MgvsProblem* p_in, const unsigned char* sel, const doubl
                                                                   : (tma_img ? bwd_stash_kernel<true, true> : bwd_stash_kernel<false, true>);
         cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, BS_SMEM_BYTES);
         kern<<<L.tiles, NT, BS_SMEM_BYTES, st>>>(sp, smaps);
-        pose_reduce_kernel<<<p->B * S, 128, 0, st>>>(L.tiles_x * L.tiles_y, sp.pose_partials, p->poses, grad_poses);
+        pose_reduce_kernel<<<p->B * S, 128, 0, st>>>(L.tiles_x * L.tiles_y, sp.pose_partials, p->pose_mats ? nullptr : p->poses, grad_poses);
         for (int i = 0; i < p->n && lowres; i++) {
             const int stride = p->H / sp.inv_h[i];
             #define MGVS_ADJ(G) launch_upsample_adjoint<G>(p->B, p->H, p->W, sp.inv_h[i], sp.inv_w[i], sp.inv_ry[i], sp.inv_rx[i], sp.grad_inv[i], adjT, grad_inv[i], st)
@@ -1027,19 +1041,22 @@ int mgvs_backward(const MgvsProblem* p_in, const unsigned char* sel, const doubl
         cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, BWD_SMEM_BYTES);
         kern<<<L.tiles, NT, BWD_SMEM_BYTES, st>>>(bp, maps);
     }
-    pose_reduce_kernel<<<p->B * S, 128, 0, st>>>(L.tiles_x * L.tiles_y, bp.pose_partials, p->poses, grad_poses);
+    pose_reduce_kernel<<<p->B * S, 128, 0, st>>>(L.tiles_x * L.tiles_y, bp.pose_partials, p->pose_mats ? nullptr : p->poses, grad_poses);
     return check_launch("mgvs_backward");
 }
 
 int mgvs_view_synthesis_ex(int B, int H, int W, const float* ref_image, const float* depth, const float* camera,
-                           long long cam_batch_stride, long long cam_row_stride, const float* pose34, int padding_mode,
+                           long long cam_batch_stride, long long cam_row_stride, const float* camera_lift,
+                           long long lift_batch_stride, long long lift_row_stride, const float* pose34, int padding_mode,
                            float* warped, float* coords, void* cuda_stream)
 {
     if (B < 1 || H < 2 || W < 2 || !ref_image || !depth || !camera || !pose34 || !warped) return fail(MGVS_EINVAL, "bad argument");
     if (padding_mode < 0 || padding_mode > 2) return fail(MGVS_EINVAL, "padding_mode must be 0 (zeros), 1 (border) or 2 (reflection)");
+    if (!camera_lift) { camera_lift = camera; lift_batch_stride = cam_batch_stride; lift_row_stride = cam_row_stride; }
     long long total = (long long)B * H * W;
     view_synthesis_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)cuda_stream>>>(
-        B, H, W, ref_image, depth, camera, cam_batch_stride, cam_row_stride, pose34, warped, coords, padding_mode);
+        B, H, W, ref_image, depth, camera, cam_batch_stride, cam_row_stride, camera_lift, lift_batch_stride, lift_row_stride,
+        pose34, warped, coords, padding_mode);
     return check_launch("mgvs_view_synthesis");
 }
 
@@ -1047,7 +1064,7 @@ int mgvs_view_synthesis(int B, int H, int W, const float* ref_image, const float
                         long long cam_batch_stride, long long cam_row_stride, const float* pose34, float* warped,
                         float* coords, void* cuda_stream)
 {
-    return mgvs_view_synthesis_ex(B, H, W, ref_image, depth, camera, cam_batch_stride, cam_row_stride, pose34, 0, warped, coords, cuda_stream);
+    return mgvs_view_synthesis_ex(B, H, W, ref_image, depth, camera, cam_batch_stride, cam_row_stride, nullptr, 0, 0, pose34, 0, warped, coords, cuda_stream);
 }
 
 int mgvs_reconstruct(int B, int H, int W, const float* depth, const float* camera, long long cam_batch_stride,

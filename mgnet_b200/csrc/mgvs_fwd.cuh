@@ -91,8 +91,13 @@ __device__ __forceinline__ void photometric4(const float* __restrict__ xs, const
             const float* xr = xs + ch * FWD_CH + dy * PITCH;
             const float* yr = ys + ch * FWD_CH + dy * PITCH;
             float4 xm = *reinterpret_cast<const float4*>(xr), ym = *reinterpret_cast<const float4*>(yr);
+#if MGVS_ABL & 8
+            float x6[6] = {xm.y, xm.x, xm.y, xm.z, xm.w, xm.z};
+            float y6[6] = {ym.y, ym.x, ym.y, ym.z, ym.w, ym.z};
+#else
             float x6[6] = {xr[-1], xm.x, xm.y, xm.z, xm.w, xr[4]};
             float y6[6] = {yr[-1], ym.x, ym.y, ym.z, ym.w, yr[4]};
+#endif
             float xx6[6], xy6[6];
 #pragma unroll
             for (int j = 0; j < 6; j++) { xx6[j] = __fmul_rn(x6[j], x6[j]); xy6[j] = __fmul_rn(x6[j], y6[j]); }
@@ -357,8 +362,10 @@ __global__ void __launch_bounds__(NT, MIN_CTAS) fwd_kernel(const FwdParams p, co
             tma::mbar_wait(sBar + 1 + (i & 1), (i >> 1) & 1);
         }
         // ---- stage 1: warp both sources at every halo pixel (software pipelined, mgvs_device.cuh) ----
+#if !(MGVS_ABL & 4)
         warp_tile<1, FWD_ROWS, FWD_CH, USE_TMA, PAD>(sX, sX + FWD_TILE3_FLOATS, sI, inv, src0, src1, sCam, x0, y0, H, W, border,
                                                       wm1, hm1, rw, rh, tid, p.pad);
+#endif
         __syncthreads();
 
         // ---- stage 2: photometric maps, min/argmin, smoothness ----
@@ -372,15 +379,39 @@ __global__ void __launch_bounds__(NT, MIN_CTAS) fwd_kernel(const FwdParams p, co
         float c1[3][3][4];
         // rows below the image and column groups right of it do not exist in the stash (the backward's TMA zero-fills them)
         const bool row_ok = STASH && v < H && (x0 >> 2) + tx < p.Wg;
+#if MGVS_ABL & 2
+        for (int k = 0; k < 4; k++) { lw0[k] = sX[ty * PITCH + XOFF + 4 * tx + k]; lw1[k] = sX[FWD_TILE3_FLOATS + ty * PITCH + XOFF + 4 * tx + k]; }
+        for (int ch = 0; ch < 3; ch++) for (int m = 0; m < 3; m++) for (int k = 0; k < 4; k++) c1[ch][m][k] = lw1[k];
+        if (STASH) st = p.stash + ((size_t)i * p.B + b) * 3 * st_ch + (size_t)v * 4 * p.Wg + (x0 >> 2) + tx;
+        if (false) {
+#else
         if (STASH) {
+#endif
             st = p.stash + ((size_t)i * p.B + b) * 3 * st_ch + (size_t)v * 4 * p.Wg + (x0 >> 2) + tx;
+#if MGVS_ROLL_SRC
+#pragma unroll 1
+            for (int s = 0; s < 2; s++) {
+                float lw[4];
+                photometric4<true>(sX + s * FWD_TILE3_FLOATS + ty * PITCH + XOFF + 4 * tx, ys_t, yst_t, p.alpha, p.oma, lw,
+                                   [&](int ch, int k, float a, float bq, float c) {
+                                       if (s == 0) { if (row_ok) __stcs(st + ch * st_ch + k * p.Wg, make_float4(a, bq, c, 1.f)); }
+                                       else { c1[ch][0][k] = a; c1[ch][1][k] = bq; c1[ch][2][k] = c; }
+                                   });
+#pragma unroll
+                for (int k = 0; k < 4; k++) { if (s == 0) lw0[k] = lw[k]; else lw1[k] = lw[k]; }
+            }
+            if (false)
+#endif
             photometric4<true>(sX + ty * PITCH + XOFF + 4 * tx, ys_t, yst_t, p.alpha, p.oma, lw0,
                                [&](int ch, int k, float a, float bq, float c) {
                                    if (row_ok) __stcs(st + ch * st_ch + k * p.Wg, make_float4(a, bq, c, 1.f));     // streaming: written once, read once
                                });
+#if MGVS_ROLL_SRC
+            if (false)
+#endif
             photometric4<true>(sX + FWD_TILE3_FLOATS + ty * PITCH + XOFF + 4 * tx, ys_t, yst_t, p.alpha, p.oma, lw1,
                                [&](int ch, int k, float a, float bq, float c) { c1[ch][0][k] = a; c1[ch][1][k] = bq; c1[ch][2][k] = c; });
-        } else if constexpr (!L1ONLY) {
+        } else if constexpr (!L1ONLY && !(MGVS_ABL & 2)) {
             photometric4<false>(sX + ty * PITCH + XOFF + 4 * tx, ys_t, yst_t, p.alpha, p.oma, lw0, NoEmit());
             photometric4<false>(sX + FWD_TILE3_FLOATS + ty * PITCH + XOFF + 4 * tx, ys_t, yst_t, p.alpha, p.oma, lw1, NoEmit());
         }

@@ -1,7 +1,8 @@
 """Pinhole ``Camera`` with the reference's interface (mgnet/geometry/camera.py:16-182).
 
-``reconstruct`` and ``project`` run sm_100a kernels (reconstruct_kernel / project_kernel, forward only);
-CPU tensors raise.  Inside the fused loss the same arithmetic is part of fwd_kernel / bwd_kernel."""
+``reconstruct`` and ``project`` run sm_100a kernels (reconstruct_kernel / project_kernel).  They are forward
+only and raise when an input requires grad (the reference ops are differentiable; gradients of the training path
+flow through the fused loss, where the same arithmetic is part of fwd_kernel / bwd_kernel).  CPU tensors raise."""
 import ctypes
 from functools import lru_cache
 
@@ -9,7 +10,7 @@ import torch
 import torch.nn as nn
 
 from .. import _lib
-from .camera_utils import scale_intrinsics
+from .camera_utils import require_no_grad, scale_intrinsics
 from .pose import Pose
 
 __all__ = ["Camera"]
@@ -68,6 +69,7 @@ class Camera(nn.Module):
             raise ValueError("Unknown reference frame {}".format(frame))
         if not depth.is_cuda:
             raise RuntimeError("Camera.reconstruct runs only on CUDA (sm_100a); there is no CPU fallback")
+        require_no_grad("Camera.reconstruct", depth, self.K, self.Tcw.mat)
         depth = depth.float().contiguous()
         K = self.K.float().contiguous()
         pts = torch.empty(B, 3, H, W, device=depth.device, dtype=torch.float32)
@@ -84,6 +86,7 @@ class Camera(nn.Module):
             raise ValueError("Unknown reference frame {}".format(frame))
         if not X.is_cuda:
             raise RuntimeError("Camera.project runs only on CUDA (sm_100a); there is no CPU fallback")
+        require_no_grad("Camera.project", X, self.K, self.Tcw.mat)
         X = X.float().contiguous()
         K = self.K.float().contiguous()
         pose34 = self.Tcw.mat[:, :3, :4].float().contiguous() if frame == "w" else None

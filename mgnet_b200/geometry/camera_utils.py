@@ -1,7 +1,8 @@
 """Intrinsics helpers and ``view_synthesis`` with the reference's signatures
 (mgnet/geometry/camera_utils.py:10-54).  ``view_synthesis`` runs the sm_100a kernel
-``view_synthesis_kernel`` (forward only -- gradients flow through the fused loss, not through this
-stand-alone op); CPU tensors raise, there is no fallback."""
+``view_synthesis_kernel``.  It is FORWARD ONLY -- gradients of the training path flow through the fused
+loss -- and says so: an input that requires grad raises instead of silently returning a tensor without
+``grad_fn`` (the reference op is an ordinary autograd graph).  CPU tensors raise, there is no fallback."""
 import ctypes
 
 import torch
@@ -28,6 +29,15 @@ def _stream(t):
     return ctypes.c_void_p(torch.cuda.current_stream(t.device).cuda_stream)
 
 
+def require_no_grad(what, *tensors):
+    """The stand-alone geometry kernels have no backward: refuse to drop a gradient silently."""
+    if torch.is_grad_enabled() and any(isinstance(t, torch.Tensor) and t.requires_grad for t in tensors):
+        raise NotImplementedError(
+            "%s is forward-only in mgnet_b200 (the reference op is differentiable): an input requires grad.  Call it under "
+            "torch.no_grad() / on detached tensors, or take gradients through MultiViewPhotometricLoss, whose fused backward "
+            "covers this arithmetic." % what)
+
+
 def view_synthesis(ref_image, depth, ref_cam, cam, mode="bilinear", padding_mode="zeros", return_coords=False):
     assert depth.size(1) == 1
     if mode != "bilinear":
@@ -42,14 +52,19 @@ def view_synthesis(ref_image, depth, ref_cam, cam, mode="bilinear", padding_mode
     ident = torch.eye(4, device=depth.device, dtype=torch.float32)
     if not torch.equal(cam.Tcw.mat.float(), ident.expand_as(cam.Tcw.mat)):
         raise NotImplementedError("view_synthesis kernel expects the target camera at the identity pose")
+    require_no_grad("view_synthesis", ref_image, depth, ref_cam.K, ref_cam.Tcw.mat, cam.K)
     ref_image = ref_image.float().contiguous()
     depth = depth.float().contiguous()
-    K = ref_cam.K.float().contiguous()
+    K = ref_cam.K.float().contiguous()           # projects (camera_utils.py:50)
+    Kl = cam.K.float().contiguous()              # back-projects (camera_utils.py:48); differs from K for Camera.scaled users
+    if Kl.shape[0] != B or K.shape[0] != B:
+        raise ValueError("camera batch sizes (%d, %d) do not match depth (%d)" % (Kl.shape[0], K.shape[0], B))
     pose34 = ref_cam.Tcw.mat[:, :3, :4].float().contiguous()
     warped = torch.empty_like(ref_image)
     coords = torch.empty(B, H, W, 2, device=depth.device, dtype=torch.float32) if return_coords else None
     with torch.cuda.device(depth.device):
         _lib.check(_lib.lib().mgvs_view_synthesis_ex(
-            B, H, W, ref_image.data_ptr(), depth.data_ptr(), K.data_ptr(), K.stride(0), K.stride(1), pose34.data_ptr(),
+            B, H, W, ref_image.data_ptr(), depth.data_ptr(), K.data_ptr(), K.stride(0), K.stride(1),
+            Kl.data_ptr(), Kl.stride(0), Kl.stride(1), pose34.data_ptr(),
             _lib.PADDING_MODES[padding_mode], warped.data_ptr(), coords.data_ptr() if coords is not None else None, _stream(depth)), "mgvs_view_synthesis")
     return (warped, coords) if return_coords else warped

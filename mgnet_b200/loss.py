@@ -58,6 +58,11 @@ class MultiViewPhotometricLoss(nn.Module):
             raise ValueError("padding_mode must be 'zeros', 'border' or 'reflection', got %r" % (padding_mode,))
         if photometric_reduce_op not in ("min", "mean"):
             raise NotImplementedError("Unknown photometric_reduce_op: {}".format(photometric_reduce_op))
+        if photometric_reduce_op == "mean" and not (float(ssim_loss_weight) > 0):
+            # the reference averages all 3 channels of the raw L1 maps here (loss[mask].mean() on [B,3,H,W], and raises an
+            # IndexError when a [B,1,H,W] mask is passed); the two-evaluation composition below would return a per-pixel
+            # channel minimum instead -- a different number
+            raise NotImplementedError("photometric_reduce_op='mean' with ssim_loss_weight == 0 is not implemented")
         # "mean" (loss.py:242-243; only legal with automask off, :106-109) runs the fused path once per source frame with that
         # frame in both source slots -- min(L, L) = L, index 0 -- and averages the two photometric losses: exact semantics,
         # twice the cost of "min" (no shipped config selects it)
@@ -84,6 +89,10 @@ class MultiViewPhotometricLoss(nn.Module):
         pose_results = predictions["poses"]
         self.n = len(inv_depths)
         assert pose_results.shape[1] == 2, "Context and poses lists must be of same length"
+        # extension: [B,S,4,4] / [B,S,3,4] pose matrices built by the caller (e.g. torch's pose_vec2mat) instead of [B,S,6] Euler
+        # vectors -- the kernels then use the caller's rotation bits (unconditionally bit-exact selection)
+        if pose_results.dim() == 4:
+            pose_results = pose_results[:, :, :3, :4]
         # custom_fwd(cast_inputs=torch.float32) equivalent (mg_net.py:827): the op computes in fp32
         # images: float in [0,1] as in the reference, or the data loader's uint8 tensors -- then the kernels apply
         # the caller's `x.float() / 255.0` (mg_net.py:320-335) themselves, bit-identically
@@ -106,6 +115,33 @@ class MultiViewPhotometricLoss(nn.Module):
         self.last_selection = sel
         return {"loss_photometric": lp, "loss_smoothness": ls}
 
+    # The reference's helper methods (loss.py:156-294) have no stand-alone counterpart: their arithmetic is fused into the two
+    # kernels and their intermediates (warped images, per-pixel SSIM / photometric maps) never exist in memory.
+    def _fused_away(self, name, hint):
+        raise NotImplementedError(
+            "MultiViewPhotometricLoss.%s is fused into the view-synthesis kernels of mgnet_b200 and is not available as a separate "
+            "step; %s" % (name, hint))
+
+    def warp_ref_image(self, depths, ref_image, cams, ref_camera_matrix, pose):
+        """loss.py:156-167, same arguments (depths are METRIC depths, cams = [target Camera]) -- through the stand-alone
+        kernel (forward only; bit-identical to the reference on CPU)."""
+        from .geometry import Camera, view_synthesis
+        ref_cam = Camera(K=ref_camera_matrix.float(), Tcw=pose.to(ref_image.device))
+        assert len(cams) == 1
+        return [view_synthesis(ref_image, d, ref_cam, cams[0], padding_mode=self.padding_mode) for d in depths]
+
+    def calc_photometric_loss(self, t_est, images):
+        self._fused_away("calc_photometric_loss", "call forward(); per-pixel maps are available from the CPU oracle (oracle/) for debugging")
+
+    def ssim(self, x, y, kernel_size=3, c1=1e-4, c2=9e-4):
+        self._fused_away("ssim", "call forward()")
+
+    def reduce_photometric_loss(self, photometric_losses, mask=None):
+        self._fused_away("reduce_photometric_loss", "call forward(); the per-scale argmin is in self.last_selection")
+
+    def calc_smoothness_loss(self, inv_depths, images, mask=None):
+        self._fused_away("calc_smoothness_loss", "call forward() and read 'loss_smoothness'")
+
     def _forward_mean(self, predictions, targets, img):
         """photometric_reduce_op="mean" (loss.py:242-243): sum_s masked_mean(L_s) / S per scale, averaged over scales -- linear in
         the per-source losses, so it is the average of two fused "min" evaluations that each see ONE source frame in both slots
@@ -115,6 +151,8 @@ class MultiViewPhotometricLoss(nn.Module):
         cfg = dataclasses.replace(self._config(), photometric_reduce_op="min", automask_loss=False)
         inv = [d.float() for d in predictions["depth"]]
         poses = predictions["poses"].float()
+        if poses.dim() == 4:
+            poses = poses[:, :, :3, :4]
         mask = targets["reprojection_mask"] if "reprojection_mask" in targets else None
         tgt = img(targets["image_orig"])
         K = targets["camera_matrix"].float()

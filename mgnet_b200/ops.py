@@ -92,7 +92,10 @@ def _fill_problem(prob, cfg, tgt, prev, nxt, inv, camera, poses, mask, ws, stash
     prob.camera = camera.data_ptr()
     prob.cam_batch_stride = camera.stride(0)
     prob.cam_row_stride = camera.stride(1)
-    prob.poses = poses.data_ptr()
+    if poses.dim() == 4:                      # [B,S,3,4] pose matrices the caller built (MgvsProblem.pose_mats)
+        prob.poses, prob.pose_mats = None, poses.data_ptr()
+    else:
+        prob.poses, prob.pose_mats = poses.data_ptr(), None
     prob.mask = mask.data_ptr() if mask is not None else None
     prob.ssim_weight = float(cfg.ssim_loss_weight)
     prob.one_minus_ssim_weight = 1.0 - float(cfg.ssim_loss_weight)   # Python double, rounded to fp32 by ctypes
@@ -148,7 +151,9 @@ class _ViewSynthesisLoss(torch.autograd.Function):
             inv = checked
         else:
             inv = [_require_cuda_f32(d, "depth[%d]" % i, (B, 1, H, W)) for i, d in enumerate(inv)]
-        poses = _require_cuda_f32(poses, "poses", (B, 2, 6))
+        # [B,S,6] Euler vectors (the reference's contract, loss.py:117-119) or [B,S,3,4] matrices = rows 0..2 of what
+        # Pose.from_vec(vec, "euler") builds (pose.py:41-47): then the kernels use the caller's rotation bits as they are
+        poses = _require_cuda_f32(poses, "poses", (B, 2, 3, 4) if poses.dim() == 4 else (B, 2, 6))
         if camera.dim() != 3 or camera.shape[0] != B or camera.shape[1] < 3 or camera.shape[2] < 3:
             raise ValueError("camera_matrix must be [B,>=3,>=3]")
         camera = _require_cuda_f32(camera, "camera_matrix")
@@ -196,9 +201,11 @@ class _ViewSynthesisLoss(torch.autograd.Function):
         ctx.cfg = cfg
         ctx.n = n
         ctx.has_mask = mask is not None
-        ctx.stash = stash            # raw scratch, not a differentiable tensor: kept on ctx like the workspace semantics
+        ctx.has_stash = stash is not None
         ctx.grad_scale = float(world) if (cfg.ddp_grad_scale and cfg.process_group is not None) else 1.0
-        saved = [poses, camera, tgt, prev, nxt, sel, sums, ws] + ([mask] if mask is not None else []) + list(inv)
+        # the stash rides with the saved tensors: freed with them after backward (retain_graph=False), alive for a second
+        # backward over the same graph (retain_graph=True) -- the same kernel runs both times
+        saved = [poses, camera, tgt, prev, nxt, sel, sums, ws] + ([mask] if mask is not None else []) + ([stash] if stash is not None else []) + list(inv)
         ctx.save_for_backward(*saved)
         ctx.mark_non_differentiable(sel)
         ctx.set_materialize_grads(False)
@@ -214,8 +221,12 @@ class _ViewSynthesisLoss(torch.autograd.Function):
         k = 8
         mask = None
         if ctx.has_mask:
-            mask = saved[8]
-            k = 9
+            mask = saved[k]
+            k += 1
+        stash = None
+        if ctx.has_stash:
+            stash = saved[k]
+            k += 1
         inv = list(saved[k:])
         dev = tgt.device
         with torch.cuda.device(dev):
@@ -229,13 +240,12 @@ class _ViewSynthesisLoss(torch.autograd.Function):
             grads = [torch.empty_like(d) for d in inv]
             gp = torch.empty_like(poses)
             prob = _lib.MgvsProblem()
-            _fill_problem(prob, ctx.cfg, tgt, prev, nxt, inv, camera, poses, mask, ws, ctx.stash)
+            _fill_problem(prob, ctx.cfg, tgt, prev, nxt, inv, camera, poses, mask, ws, stash)
             arr = (ctypes.c_void_p * len(grads))(*[x.data_ptr() for x in grads])
             stream = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
             _lib.check(L.mgvs_backward(ctypes.byref(prob), sel.data_ptr(), sums.data_ptr(), g.data_ptr(), arr,
                                        gp.data_ptr(), stream), "mgvs_backward")
             launch_counter.n += BWD_LAUNCHES + (2 * len(inv) if ctx.cfg.fuse_upsample else 0)   # + two upsample-adjoint kernels per scale
-        ctx.stash = None
         return (None, gp, None, None, None, None, None) + tuple(grads)
 
 

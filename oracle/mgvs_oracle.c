@@ -45,6 +45,8 @@ typedef struct {
     float ssim_w, photo_w, smooth_w;
     int automask;
     int padding_mode;               /* grid_sample padding_mode (camera_utils.py:52-54): 0 zeros, 1 border, 2 reflection */
+    const float *pose_mats;         /* optional [B,S,3,4] row-major (R|t) = rows 0..2 of Pose.mat (pose.py:41-47); when non-NULL it
+                                       replaces the Euler evaluation of `poses` (the caller built R, e.g. with torch's pose_vec2mat) */
 } OrcIn;
 
 typedef struct {
@@ -94,6 +96,10 @@ static void orc_prep_cam(const OrcIn *in, int b, float K[9], float Kinv[9], floa
     Kinv[2] = (-1.0f * cx) / fx;
     Kinv[5] = (-1.0f * cy) / fy;
     for (int s = 0; s < ORC_S; s++) {
+        if (in->pose_mats) {
+            memcpy(Rt[s], in->pose_mats + ((long)b * ORC_S + s) * 12, 12 * sizeof(float));
+            continue;
+        }
         const float *v = in->poses + ((long)b * ORC_S + s) * 6;
         float cxr = (float)cos((double)v[3]), sxr = (float)sin((double)v[3]);
         float cyr = (float)cos((double)v[4]), syr = (float)sin((double)v[4]);
@@ -653,6 +659,11 @@ int orc_backward(const OrcIn *in, double ssim_w_double, int euler_fma, const uin
         }
         /* Euler chain: R = Rx Ry Rz (pose_utils.py:14-38), vec = (tx,ty,tz,rx,ry,rz) */
         for (int s = 0; s < S; s++) {
+            if (in->pose_mats) {     /* matrix input: the gradient is dL/d(R|t) itself (grad_Rt); no Euler chain */
+                if (grad_poses) for (int k = 0; k < 6; k++) grad_poses[((long)b * S + s) * 6 + k] = 0.0f;
+                if (grad_Rt) memcpy(grad_Rt + ((long)b * S + s) * 12, gRt[s], sizeof(double) * 12);
+                continue;
+            }
             const float *vv = in->poses + ((long)b * S + s) * 6;
             double cx = cos((double)vv[3]), sx = sin((double)vv[3]);
             double cy = cos((double)vv[4]), sy = sin((double)vv[4]);
@@ -681,4 +692,4 @@ int orc_backward(const OrcIn *in, double ssim_w_double, int euler_fma, const uin
     return 0;
 }
 
-int orc_abi_version(void) { return 1; }
+int orc_abi_version(void) { return 2; }

@@ -53,6 +53,7 @@ class _OrcIn(ctypes.Structure):
         ("ssim_w", ctypes.c_float), ("photo_w", ctypes.c_float), ("smooth_w", ctypes.c_float),
         ("automask", ctypes.c_int),
         ("padding_mode", ctypes.c_int),
+        ("pose_mats", ctypes.c_void_p),
     ]
 
 
@@ -108,6 +109,11 @@ class Oracle:
         self.n = len(self.inv)
         self.B, _, self.H, self.W = self.inv[0].shape
         self.poses = _np(predictions["poses"])
+        # [B,S,6] Euler vectors (the reference's contract) or [B,S,3,4] / [B,S,4,4] pose matrices the caller built
+        self.pose_mats = None
+        if self.poses.ndim == 4:
+            self.pose_mats = np.ascontiguousarray(self.poses[:, :, :3, :4])
+            self.poses = np.zeros((self.poses.shape[0], S, 6), np.float32)
         self.tgt = _np(targets["image_orig"])
         self.src = [_np(targets["image_prev_orig"]), _np(targets["image_next_orig"])]
         self.cam = _np(targets["camera_matrix"])
@@ -133,6 +139,7 @@ class Oracle:
         i.ssim_w, i.photo_w, i.smooth_w = self.ssim_w, self.photo_w, self.smooth_w
         i.automask = int(self.automask)
         i.padding_mode = {"zeros": 0, "border": 1, "reflection": 2}[padding_mode]
+        i.pose_mats = _ptr(self.pose_mats) if self.pose_mats is not None else None
         self.sums = None
         self.sel = None
 

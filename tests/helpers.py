@@ -24,15 +24,27 @@ def golden_names():
 def load_golden(name):
     """Returns (predictions, targets, hyper-parameters, reference outputs) with CPU tensors."""
     z = np.load(os.path.join(GOLDEN, name + ".npz"))
-    n = len([k for k in z.files if k.startswith("in_depth_")])
+
+    def image(key):
+        # compact fixtures (make_golden_c1.py) hold the data loader's uint8; the loss sees u8.float() / 255 (mg_net.py:320-335)
+        if "in_u8_" + key in z.files:
+            return (torch.from_numpy(z["in_u8_" + key]).float() / 255.0).contiguous()
+        return torch.from_numpy(z["in_" + key])
+
+    def depth(i):
+        if "in_f16_depth_%d" % i in z.files:       # fp16-representable values, stored as fp16
+            return torch.from_numpy(z["in_f16_depth_%d" % i]).float().contiguous()
+        return torch.from_numpy(z["in_depth_%d" % i])
+
+    n = len([k for k in z.files if k.startswith(("in_depth_", "in_f16_depth_"))])
     pred = {
-        "depth": [torch.from_numpy(z["in_depth_%d" % i]) for i in range(n)],
+        "depth": [depth(i) for i in range(n)],
         "poses": torch.from_numpy(z["in_poses"]),
     }
     tgt = {
-        "image_orig": torch.from_numpy(z["in_image_orig"]),
-        "image_prev_orig": torch.from_numpy(z["in_image_prev_orig"]),
-        "image_next_orig": torch.from_numpy(z["in_image_next_orig"]),
+        "image_orig": image("image_orig"),
+        "image_prev_orig": image("image_prev_orig"),
+        "image_next_orig": image("image_next_orig"),
         "camera_matrix": torch.from_numpy(z["in_camera_matrix"]),
     }
     if "in_reprojection_mask" in z.files:
