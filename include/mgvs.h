@@ -182,6 +182,10 @@ int mgvs_project(int B, int H, int W, const float *points, const float *camera, 
  * zero-filled once, before the first call on any rank (barrier in between), and every rank must make the same sequence of
  * calls.  The reference under DDP has no such exchange (each rank normalises by its local mask count). */
 #define MGVS_MAX_RANKS 16
+/* Byte offset, in the LOCAL exchange buffer, of a 64-bit status word: 0 while every exchange completed; otherwise the step
+ * number of the first call whose peers did not all arrive within the wait bound (>= 40 s; unequal call sequences across
+ * ranks).  That call writes NaN into `losses` and returns normally -- no device trap, the CUDA context stays usable. */
+#define MGVS_EXCHANGE_STATUS_OFFSET 8
 typedef struct MgvsPeerExchange {
     int rank, world;                    /* 1 <= world <= MGVS_MAX_RANKS */
     void *peer_base[MGVS_MAX_RANKS];    /* >= mgvs_exchange_bytes() each, 16-byte aligned; peer_base[rank] is the local one */

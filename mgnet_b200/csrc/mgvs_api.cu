@@ -669,11 +669,12 @@ static int check_launch(const char* what)
 
 
 // ---- sharded batch: push-based all-reduce of the 3n+3 partial sums over peer memory + finalize, one launch -------------
-// Buffer layout (per rank, symmetric): [0] step counter (local use), [64 + 8*(g*MAX_RANKS + r)] flag of rank r in
+// Buffer layout (per rank, symmetric): [0] step counter (local use), [8] status word (MGVS_EXCHANGE_STATUS_OFFSET), [64 + 8*(g*MAX_RANKS + r)] flag of rank r in
 // generation g, [1024 + 8*((g*MAX_RANKS + r)*32 + j)] value j of rank r in generation g.  Generation = step & 1: a rank can
 // run at most one step ahead of the slowest one (it needs everybody's flag of step k to leave step k), so two generations
 // never collide.
 constexpr int XCH_FLAGS_OFF = 64, XCH_DATA_OFF = 1024, XCH_VALS = 32;
+constexpr int XCH_STATUS_WORD = 1;      // u64 index in the local buffer: 0 = fine, else the first step whose exchange timed out
 constexpr size_t XCH_BYTES = XCH_DATA_OFF + (size_t)2 * MGVS_MAX_RANKS * XCH_VALS * sizeof(double);
 struct PeerPtrs { char* base[MGVS_MAX_RANKS]; };
 
@@ -696,6 +697,7 @@ __global__ void __launch_bounds__(256) exchange_finalize_kernel(int n, int rank,
                                                                 float photo_w, float smooth_w, float* __restrict__ losses)
 {
     __shared__ unsigned long long s_step;
+    __shared__ int s_timeout;
     __shared__ double s_sums[XCH_VALS];
     const int tid = threadIdx.x, m = 3 * n + 3;
     char* mine = peers.base[rank];
@@ -703,6 +705,7 @@ __global__ void __launch_bounds__(256) exchange_finalize_kernel(int n, int rank,
         unsigned long long* ctr = reinterpret_cast<unsigned long long*>(mine);
         s_step = *ctr + 1ull;
         *ctr = s_step;
+        s_timeout = 0;
     }
     __syncthreads();
     const unsigned long long step = s_step;
@@ -719,14 +722,22 @@ __global__ void __launch_bounds__(256) exchange_finalize_kernel(int n, int rank,
     if (tid < world) {
         st_release_sys(reinterpret_cast<unsigned long long*>(peers.base[tid] + XCH_FLAGS_OFF) + (g * MGVS_MAX_RANKS + rank), step);
         const unsigned long long* f = reinterpret_cast<const unsigned long long*>(mine + XCH_FLAGS_OFF) + (g * MGVS_MAX_RANKS + tid);
-        // bounded: a rank that never arrives (unequal call sequences) becomes a launch failure after >= 40 s instead of a hung GPU
+        // bounded: a rank that never arrives (unequal call sequences) ends the wait after >= 40 s; the kernel then reports
+        // instead of trapping (a trap would poison the CUDA context): NaN losses + the step number in the status word
         unsigned long long spins = 0;
         while (ld_acquire_sys(f) != step) {
             __nanosleep(20);
-            if (++spins > (1ull << 31)) __trap();
+            if (++spins > (1ull << 31)) { s_timeout = 1; break; }
         }
     }
     __syncthreads();
+    if (s_timeout) {
+        if (tid == 0) {
+            reinterpret_cast<unsigned long long*>(mine)[XCH_STATUS_WORD] = step;
+            losses[0] = __int_as_float(0x7fc00000); losses[1] = __int_as_float(0x7fc00000);
+        }
+        return;
+    }
     // 4. the world's vectors in rank order: deterministic and the same bits on every rank
     if (tid < m) {
         double acc = 0.0;

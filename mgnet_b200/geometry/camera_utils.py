@@ -49,8 +49,8 @@ def view_synthesis(ref_image, depth, ref_cam, cam, mode="bilinear", padding_mode
     B, _, H, W = depth.shape
     # target camera pose must be the identity as in the loss (cams[0], loss.py:127): the kernel lifts
     # with K^-1 only and applies ref_cam.Tcw
-    ident = torch.eye(4, device=depth.device, dtype=torch.float32)
-    if not torch.equal(cam.Tcw.mat.float(), ident.expand_as(cam.Tcw.mat)):
+    tcw = cam.Tcw.mat.float()                    # may still live on the CPU (Camera(K) builds its identity pose there)
+    if not torch.equal(tcw, torch.eye(4, device=tcw.device, dtype=torch.float32).expand_as(tcw)):
         raise NotImplementedError("view_synthesis kernel expects the target camera at the identity pose")
     require_no_grad("view_synthesis", ref_image, depth, ref_cam.K, ref_cam.Tcw.mat, cam.K)
     ref_image = ref_image.float().contiguous()

@@ -78,3 +78,10 @@ class PeerExchange:
         for r, ptr in enumerate(self.handle.buffer_ptrs):
             x.peer_base[r] = int(ptr)
         self.struct = x
+
+    def check(self) -> None:
+        """Raises if an exchange on this rank ever timed out (MGVS_EXCHANGE_STATUS_OFFSET, include/mgvs.h): the ranks made
+        unequal call sequences.  Synchronises the device -- call it outside the step's critical path (e.g. once per epoch)."""
+        step = int(self.buffer[1].item())
+        if step != 0:
+            raise RuntimeError("mgvs_exchange_finalize timed out at step %d on rank %d: not every rank called it (losses were NaN)" % (step, self.rank))

@@ -103,7 +103,7 @@ def test_reconstruct_matches_reference_formula(shape):
     B, H, W = shape
     pred, tgt, K, depth = _inputs(B, H, W)
     ref_c = (_kinv(K).bmm(_pixel_grid(B, H, W, torch.float32, torch.device("cpu")).view(B, 3, -1)) * depth.view(B, 1, -1)).view(B, 3, H, W)
-    cam = Camera(K.to(dev))
+    cam = Camera(K.to(dev)).to(dev)                                                # as the reference's callers do: the identity Tcw is made on the CPU
     out_c = cam.reconstruct(depth.to(dev), frame="c")
     assert np.array_equal(out_c.cpu().numpy(), ref_c.numpy())                      # camera.py:129-136, bit for bit
     assert torch.equal(cam.reconstruct(depth.to(dev), frame="w"), out_c)           # identity Tcw: Twc @ X is exact
