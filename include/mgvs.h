@@ -23,12 +23,23 @@
 extern "C" {
 #endif
 
-#define MGVS_ABI_VERSION 6   /* v2 image_dtype, v3 stash, v4 inv_height/inv_width, v5 padding modes, ssim_weight == 0, DGC, uncertainty, peer exchange,
-                                v6 pose_mats, camera_lift of mgvs_view_synthesis_ex, differentiable geometry ops, pose tail, exchange status */
+#define MGVS_ABI_VERSION 7   /* v2 image_dtype, v3 stash, v4 inv_height/inv_width, v5 padding modes, ssim_weight == 0, DGC, uncertainty, peer exchange,
+                                v6 pose_mats, camera_lift of mgvs_view_synthesis_ex, differentiable geometry ops, pose tail, exchange status,
+                                v7 forward_mode (margin-gated fast SSIM evaluation), mgvs_forward_diag */
 #define MGVS_MAX_SCALES 8   /* n: number of inverse-depth maps (reference: 3, mg_net.py:760-764) */
 #define MGVS_NUM_SOURCES 2  /* S: prev, next -- hard-coded in the reference (loss.py:116) */
 
 enum { MGVS_IMAGE_F32 = 0, MGVS_IMAGE_U8 = 1 };
+
+/* MgvsProblem.forward_mode: how the forward evaluates the per-pixel photometric losses of the warped sources.
+ *   MGVS_FORWARD_EXACT (default)  the reference's fp32 rounding sequence at every pixel
+ *   MGVS_FORWARD_GATED            separable-sum / FMA-contracted SSIM with a per-pixel error bound; every pixel whose minimum is
+ *                                 not separated from the other candidates by more than the bounds is re-evaluated with the exact
+ *                                 chain, so `sel` is still bit-exact and the losses agree with the exact evaluation to ~1e-7
+ *                                 relative.  Measured SLOWER than EXACT on B200 (the gate costs more than the evaluation saves,
+ *                                 DESIGN.md section 5a); kept as a tested option, not the default.
+ *   MGVS_FORWARD_RECHECK_ALL      tests only: the gated kernel with every pixel treated as a near-tie (sums bit-identical to EXACT) */
+enum { MGVS_FORWARD_EXACT = 0, MGVS_FORWARD_GATED = 1, MGVS_FORWARD_RECHECK_ALL = 2 };
 
 enum {
     MGVS_OK = 0,
@@ -95,6 +106,7 @@ typedef struct MgvsProblem {
                                    (torch-CPU sin/cos are MKL-VML values, 1 ulp off the correctly rounded ones the kernel uses for ~5 %
                                    of arguments), so the selection mask is bit-exact for ANY angles.  mgvs_backward then writes
                                    grad_poses as [B,S,3,4] = dL/d(R|t) (no Euler chain; autograd of the caller's pose_vec2mat does it). */
+    int forward_mode;           /* MGVS_FORWARD_* (0 = exact, the default) */
 } MgvsProblem;
 
 int mgvs_abi_version(void);
@@ -127,6 +139,12 @@ int mgvs_num_sums(int n);
  *        With ssim_weight == 0 every list entry has 3 channels and the index is entry * 3 + channel (0..11).
  *   sums [3n+3] double out: this rank's partial sums (see above). */
 int mgvs_forward(const MgvsProblem *p, unsigned char *sel, double *sums, void *cuda_stream);
+
+/* Statistics of the last mgvs_forward on this workspace (MGVS_FORWARD_GATED / RECHECK_ALL): *diag_dev receives a DEVICE pointer
+ * into p->workspace to three 64-bit words, [0] pixels (summed over scales) that were re-evaluated with the exact chain, [1] how
+ * many of those changed their selection, [2] the fp32 bit pattern of max |fast - exact| / bound over the re-evaluated pixels (the
+ * bound is sound while this stays below 1).  Valid once the forward's launches have completed; the caller copies them. */
+int mgvs_forward_diag(const MgvsProblem *p, const unsigned long long **diag_dev);
 
 /* Single-rank convenience: mgvs_forward followed by mgvs_finalize in the same launches (the last block of the
  * reduction also writes the two losses).  losses [2] float out; NULL behaves exactly like mgvs_forward. */

@@ -15,8 +15,10 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _CSRC = os.path.join(_HERE, "csrc")
 LIB_PATH = os.environ.get("MGVS_LIB_PATH") or os.path.join(_HERE, "libmgvs.so")   # override: kernel-variant experiments only
 MAX_SCALES = 8
-ABI_VERSION = 6
+ABI_VERSION = 7
 IMAGE_F32, IMAGE_U8 = 0, 1
+FORWARD_EXACT, FORWARD_GATED, FORWARD_RECHECK_ALL = 0, 1, 2
+FORWARD_MODES = {"gated": FORWARD_GATED, "exact": FORWARD_EXACT, "recheck_all": FORWARD_RECHECK_ALL}
 NUM_SOURCES = 2
 
 NVCC_FLAGS = [
@@ -43,6 +45,7 @@ class MgvsProblem(ctypes.Structure):
         ("stash", ctypes.c_void_p), ("stash_bytes", ctypes.c_size_t),
         ("inv_height", ctypes.c_int * MAX_SCALES), ("inv_width", ctypes.c_int * MAX_SCALES),
         ("pose_mats", ctypes.c_void_p),
+        ("forward_mode", ctypes.c_int),
     ]
 
 
@@ -147,6 +150,8 @@ def lib():
     L.mgvs_stash_bytes_ex.argtypes = [ci, ci, ci, ci, ci]
     L.mgvs_forward.restype = ci
     L.mgvs_forward.argtypes = [PP, vp, vp, vp]
+    L.mgvs_forward_diag.restype = ci
+    L.mgvs_forward_diag.argtypes = [PP, ctypes.POINTER(vp)]
     L.mgvs_forward_losses.restype = ci
     L.mgvs_forward_losses.argtypes = [PP, vp, vp, vp, vp]
     L.mgvs_finalize.restype = ci
@@ -185,7 +190,7 @@ def lib():
 
 
 EXPORTED_SYMBOLS = (
-    "mgvs_abi_version", "mgvs_last_error", "mgvs_num_sums", "mgvs_workspace_bytes", "mgvs_workspace_bytes_ex", "mgvs_stash_bytes", "mgvs_stash_bytes_ex", "mgvs_forward", "mgvs_forward_losses",
+    "mgvs_abi_version", "mgvs_last_error", "mgvs_num_sums", "mgvs_workspace_bytes", "mgvs_workspace_bytes_ex", "mgvs_stash_bytes", "mgvs_stash_bytes_ex", "mgvs_forward", "mgvs_forward_diag", "mgvs_forward_losses",
     "mgvs_finalize", "mgvs_backward", "mgvs_view_synthesis", "mgvs_view_synthesis_ex", "mgvs_reconstruct", "mgvs_project", "mgvs_test_div",
     "mgvs_dgc_workspace_bytes", "mgvs_dgc_rescale", "mgvs_dgc_heights",
     "mgvs_uncertainty_forward", "mgvs_uncertainty_backward",

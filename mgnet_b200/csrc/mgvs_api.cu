@@ -623,6 +623,7 @@ static int check_problem(const MgvsProblem* p)
     for (int i = 0; i < p->n; i++)
         if (!p->inv_depth[i]) return fail(MGVS_EINVAL, "null inverse-depth pointer");
     if (p->padding_mode < 0 || p->padding_mode > 2) return fail(MGVS_EINVAL, "padding_mode must be 0 (zeros), 1 (border) or 2 (reflection)");
+    if (p->forward_mode < 0 || p->forward_mode > 2) return fail(MGVS_EINVAL, "forward_mode must be MGVS_FORWARD_GATED, _EXACT or _RECHECK_ALL");
     if (p->reduce_op != 0) return fail(MGVS_EUNSUPPORTED, "photometric_reduce_op: the kernels implement 'min'; 'mean' is composed from two 'min' evaluations by the caller (mgnet_b200/loss.py)");
     if (!(p->ssim_weight >= 0.f)) return fail(MGVS_EINVAL, "ssim_loss_weight must be >= 0");
     if (!(p->ssim_weight > 0.f) && lowres_mode(p) != 0) return fail(MGVS_EUNSUPPORTED, "fused upsample with ssim_loss_weight == 0 (it needs the coefficient stash, which the L1-only branch does not have)");
@@ -912,16 +913,21 @@ int mgvs_forward_losses(const MgvsProblem* p_in, unsigned char* sel, double* sum
         fp.inv_rx[i] = p->W > 1 ? (float)((double)(p->inv_width[i] - 1) / (double)(p->W - 1)) : 0.f;
     }
     fp.early_wait = u8 ? 1 : 0;
+    fp.flag_all = p->forward_mode == MGVS_FORWARD_RECHECK_ALL;
+    fp.diag = (unsigned long long*)(ws + L.counter + 64);
     if (!use_tma) memset(&maps, 0, sizeof(maps));
     fp.stash = (float4*)p->stash; fp.Wg = (p->W + 3) / 4;
     fp.wgt = p->stash ? (float*)((char*)p->stash + stash_texel_bytes(p->B, p->H, p->W, p->n)) : nullptr;
     {
-        // padding_mode "zeros" runs the PAD = false instantiations (unchanged code); "border" / "reflection" the PAD = true ones
-        void (*kern)(FwdParams, FwdMaps) =
-            p->padding_mode == 0 ? (use_tma ? (p->stash ? fwd_kernel<true, true> : fwd_kernel<true, false>)
-                                            : (p->stash ? fwd_kernel<false, true> : fwd_kernel<false, false>))
-                                 : (use_tma ? (p->stash ? fwd_kernel<true, true, true> : fwd_kernel<true, false, true>)
-                                            : (p->stash ? fwd_kernel<false, true, true> : fwd_kernel<false, false, true>));
+        // padding_mode "zeros" runs the PAD = false instantiations (unchanged code); "border" / "reflection" the PAD = true ones.
+        // forward_mode EXACT (default): the exact chain everywhere; GATED / RECHECK_ALL: margin-gated fast SSIM evaluation with exact
+        // re-evaluation of near-ties (measured slower)
+        #define MGVS_FWD_PICK(FAST) (p->padding_mode == 0 ? (use_tma ? (p->stash ? fwd_kernel<true, true, false, false, FAST> : fwd_kernel<true, false, false, false, FAST>) \
+                                                                      : (p->stash ? fwd_kernel<false, true, false, false, FAST> : fwd_kernel<false, false, false, false, FAST>)) \
+                                                           : (use_tma ? (p->stash ? fwd_kernel<true, true, true, false, FAST> : fwd_kernel<true, false, true, false, FAST>) \
+                                                                      : (p->stash ? fwd_kernel<false, true, true, false, FAST> : fwd_kernel<false, false, true, false, FAST>)))
+        void (*kern)(FwdParams, FwdMaps) = p->forward_mode == MGVS_FORWARD_EXACT ? MGVS_FWD_PICK(false) : MGVS_FWD_PICK(true);
+        #undef MGVS_FWD_PICK
         if (l1only)   // ssim_loss_weight == 0: raw 3-channel L1, 12-way min (loss.py:195-196); never with the stash
             kern = p->padding_mode == 0 ? (use_tma ? fwd_kernel<true, false, false, true> : fwd_kernel<false, false, false, true>)
                                         : (use_tma ? fwd_kernel<true, false, true, true> : fwd_kernel<false, false, true, true>);
@@ -937,6 +943,16 @@ int mgvs_forward_losses(const MgvsProblem* p_in, unsigned char* sel, double* sum
 int mgvs_forward(const MgvsProblem* p, unsigned char* sel, double* sums, void* cuda_stream)
 {
     return mgvs_forward_losses(p, sel, sums, nullptr, cuda_stream);
+}
+
+int mgvs_forward_diag(const MgvsProblem* p, const unsigned long long** diag_dev)
+{
+    int rc = check_problem(p);
+    if (rc) return rc;
+    if (!diag_dev) return fail(MGVS_EINVAL, "null diag_dev");
+    Layout L = make_layout(p->B, p->H, p->W, p->n, p->image_dtype);
+    *diag_dev = (const unsigned long long*)((const char*)p->workspace + L.counter + 64);
+    return MGVS_OK;
 }
 
 int mgvs_finalize(const MgvsProblem* p, const double* sums, float* losses, void* cuda_stream)

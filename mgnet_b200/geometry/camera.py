@@ -71,7 +71,7 @@ class Camera(nn.Module):
             raise RuntimeError("Camera.reconstruct runs only on CUDA (sm_100a); there is no CPU fallback")
         require_no_grad("Camera.reconstruct", depth, self.K, self.Tcw.mat)
         depth = depth.float().contiguous()
-        K = self.K.float().contiguous()
+        K = self.K.to(depth.device).float().contiguous()
         pts = torch.empty(B, 3, H, W, device=depth.device, dtype=torch.float32)
         with torch.cuda.device(depth.device):
             _lib.check(_lib.lib().mgvs_reconstruct(B, H, W, depth.data_ptr(), K.data_ptr(), K.stride(0), K.stride(1),
@@ -88,8 +88,8 @@ class Camera(nn.Module):
             raise RuntimeError("Camera.project runs only on CUDA (sm_100a); there is no CPU fallback")
         require_no_grad("Camera.project", X, self.K, self.Tcw.mat)
         X = X.float().contiguous()
-        K = self.K.float().contiguous()
-        pose34 = self.Tcw.mat[:, :3, :4].float().contiguous() if frame == "w" else None
+        K = self.K.to(X.device).float().contiguous()
+        pose34 = self.Tcw.mat[:, :3, :4].to(X.device).float().contiguous() if frame == "w" else None
         coords = torch.empty(B, H, W, 2, device=X.device, dtype=torch.float32)
         with torch.cuda.device(X.device):
             _lib.check(_lib.lib().mgvs_project(B, H, W, X.data_ptr(), K.data_ptr(), K.stride(0), K.stride(1),

@@ -55,11 +55,12 @@ def view_synthesis(ref_image, depth, ref_cam, cam, mode="bilinear", padding_mode
     require_no_grad("view_synthesis", ref_image, depth, ref_cam.K, ref_cam.Tcw.mat, cam.K)
     ref_image = ref_image.float().contiguous()
     depth = depth.float().contiguous()
-    K = ref_cam.K.float().contiguous()           # projects (camera_utils.py:50)
-    Kl = cam.K.float().contiguous()              # back-projects (camera_utils.py:48); differs from K for Camera.scaled users
+    dev = depth.device                           # (a Camera built without .to(device) keeps its identity pose on the CPU)
+    K = ref_cam.K.to(dev).float().contiguous()   # projects (camera_utils.py:50)
+    Kl = cam.K.to(dev).float().contiguous()      # back-projects (camera_utils.py:48); differs from K for Camera.scaled users
     if Kl.shape[0] != B or K.shape[0] != B:
         raise ValueError("camera batch sizes (%d, %d) do not match depth (%d)" % (Kl.shape[0], K.shape[0], B))
-    pose34 = ref_cam.Tcw.mat[:, :3, :4].float().contiguous()
+    pose34 = ref_cam.Tcw.mat[:, :3, :4].to(dev).float().contiguous()
     warped = torch.empty_like(ref_image)
     coords = torch.empty(B, H, W, 2, device=depth.device, dtype=torch.float32) if return_coords else None
     with torch.cuda.device(depth.device):

@@ -1,0 +1,6 @@
+#!/bin/bash
+TAG=r02d
+mkdir -p gpurun_out
+timeout 900 python -m pytest tests/test_gated_forward.py -x -q -s 2>&1 | tail -40 | tee gpurun_out/${TAG}_pytest_gated.txt
+for rep in 1 2; do for m in exact gated; do MGVS_FORWARD_MODE=$m timeout 300 python scripts/time_kernels.py c2 c4 2>&1 | tail -1; done; done | tee gpurun_out/${TAG}_modes.txt
+timeout 1500 python -m pytest tests -x -q -m gpu --deselect tests/test_gated_forward.py 2>&1 | tail -15 | tee gpurun_out/${TAG}_pytest_gpu.txt

@@ -29,7 +29,7 @@ def test_header_symbols_exported():
 def test_host_side_queries():
     from mgnet_b200 import _lib
     L = _lib.lib()
-    assert L.mgvs_abi_version() == _lib.ABI_VERSION == 6
+    assert L.mgvs_abi_version() == _lib.ABI_VERSION == 7
     assert L.mgvs_num_sums(3) == 12
     ws = L.mgvs_workspace_bytes(16, 192, 640, 3)
     assert ws > 0 and ws % 256 == 0

@@ -193,7 +193,7 @@ def test_warp_ref_image_helper_and_fused_away_helpers():
     pred, tgt, K, depth = _inputs(B, H, W)
     mod = MultiViewPhotometricLoss(0.85, 1.0, 1e-3, True, "min", "zeros")
     pose = Pose.from_vec(pred["poses"][:, 0], "euler")
-    out = mod.warp_ref_image([depth.to(dev)], tgt["image_prev_orig"].to(dev), [Camera(K.to(dev))], K.to(dev), pose)
+    out = mod.warp_ref_image([depth.to(dev)], tgt["image_prev_orig"].to(dev), [Camera(K.to(dev))], K.to(dev), Pose(pose.mat.clone()))
     want = _synthesize(tgt["image_prev_orig"], depth, K, _kinv(K), pose.mat, torch.eye(4).repeat(B, 1, 1))
     assert len(out) == 1 and np.array_equal(out[0].cpu().numpy(), want.numpy())
     for name, args in (("ssim", (depth, depth)), ("calc_photometric_loss", ([depth], [depth])), ("reduce_photometric_loss", ([[depth]],)),
