@@ -178,6 +178,9 @@ def main():
                     help="what the e2e leg's host hands over as predictions['depth']: lowres = the depth head's low-resolution maps "
                          "(strides 8/16/32; the module upsamples them in-kernel like the head's F.interpolate and returns low-resolution "
                          "gradients: fuse_upsample=True, SURVEY 8f-1) -- 0.25 instead of 12 B/px of H2D traffic; full = full-resolution fp32 maps")
+    ap.add_argument("--e2e-mask", default="bits", choices=["bits", "bytes"],
+                    help="reprojection mask of the e2e leg's host inputs: bits = numpy.packbits bytes (unpacked on the device by mgvs_unpack_mask), "
+                         "bytes = the torch.bool tensor of the reference (1 byte per pixel)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
 
@@ -360,7 +363,7 @@ def main():
     # ---- end to end: pinned host inputs -> H2D -> module fwd+bwd -> D2H of the two losses ----
     e2e = None
     if not args.no_e2e:
-        from mgnet_b200.synthetic import quantize_images
+        from mgnet_b200.synthetic import pack_mask, quantize_images
 
         # One pinned host arena per input set and one device arena per slot: a step's inputs cross PCIe as ONE copy (the nine
         # tensors are 256-byte aligned views of the arena), so the link does not idle between per-tensor copies.
@@ -395,6 +398,8 @@ def main():
         for pred, tgt in sets_host:
             if args.e2e_images == "uint8":      # what the reference's data loader hands over (mg_net.py:320-335)
                 tgt = quantize_images(tgt)[0]
+            if args.e2e_mask == "bits" and "reprojection_mask" in tgt:
+                tgt = dict(tgt, reprojection_mask=pack_mask(tgt["reprojection_mask"]))
             if lowres:                          # what the depth head produces before its own F.interpolate (mg_net.py:799-807)
                 pred = {"depth": [F.avg_pool2d(d, st).contiguous() for d, st in zip(pred["depth"], strides)], "poses": pred["poses"]}
             items, plan, total = layout(pred, tgt)
@@ -457,12 +462,13 @@ def main():
         ms_e = float(te.item()) / args.steps
         e2e = {"value": px_step / (ms_e * 1e-3) / 1e9, "unit": "Gpixel/s", "h2d_bytes_per_step": int(h2d),
                "d2h_bytes_per_step": 8, "ms_per_step": ms_e, "wall_ms_per_step": wall_ms / args.steps,
-               "images": args.e2e_images, "depth": args.e2e_depth,
+               "images": args.e2e_images, "depth": args.e2e_depth, "mask": args.e2e_mask,
                "h2d_gbs_per_rank": h2d / (ms_e * 1e-3) / 1e9,
-               "note": "pinned host inputs (images as %s; inverse depth as %s) in one arena -> ONE H2D copy per step, overlapped with the compute of the previous step on a copy stream" % (
+               "note": "pinned host inputs (images as %s; inverse depth as %s; reprojection mask as %s) in one arena -> ONE H2D copy per step, overlapped with the compute of the previous step on a copy stream" % (
                    "the data loader's uint8, converted in-kernel like the reference's x.float()/255" if args.e2e_images == "uint8" else "float32",
-                   "the depth head's low-resolution fp32 maps (strides %s), upsampled in-kernel bit-identically to its F.interpolate(bilinear, align_corners=True); "
-                   "gradients return at low resolution (fuse_upsample=True)" % (list(strides),) if lowres else "full-resolution fp32 maps")}
+                   ("the depth head's low-resolution fp32 maps (strides %s), upsampled in-kernel bit-identically to its F.interpolate(bilinear, align_corners=True); "
+                    "gradients return at low resolution (fuse_upsample=True)" % (list(strides),)) if lowres else "full-resolution fp32 maps",
+                   "numpy.packbits bytes, unpacked on the device (mgvs_unpack_mask)" if args.e2e_mask == "bits" else "torch.bool bytes")}
 
     clocks = sampler.stop() if rank == 0 else None
 

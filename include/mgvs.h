@@ -25,7 +25,7 @@ extern "C" {
 
 #define MGVS_ABI_VERSION 7   /* v2 image_dtype, v3 stash, v4 inv_height/inv_width, v5 padding modes, ssim_weight == 0, DGC, uncertainty, peer exchange,
                                 v6 pose_mats, camera_lift of mgvs_view_synthesis_ex, differentiable geometry ops, pose tail, exchange status,
-                                v7 forward_mode (margin-gated fast SSIM evaluation), mgvs_forward_diag */
+                                v7 forward_mode (margin-gated fast SSIM evaluation), mgvs_forward_diag, mgvs_unpack_mask */
 #define MGVS_MAX_SCALES 8   /* n: number of inverse-depth maps (reference: 3, mg_net.py:760-764) */
 #define MGVS_NUM_SOURCES 2  /* S: prev, next -- hard-coded in the reference (loss.py:116) */
 
@@ -268,6 +268,12 @@ int mgvs_uncertainty_forward(int k, const float *raw, const float *log_vars, con
 /*   g_weighted [k] in;  g_raw [k] = g * tau * exp(-s);  g_log_vars [k] = g * (0.5 - tau * exp(-s) * raw) */
 int mgvs_uncertainty_backward(int k, const float *raw, const float *log_vars, const float *tau_host,
                               const float *g_weighted, float *g_raw, float *g_log_vars, void *cuda_stream);
+
+/* Bit-packed reprojection mask -> the byte-per-pixel bool tensor MgvsProblem.mask expects.  `bits` is numpy.packbits(mask, axis=-1):
+ * most significant bit first, every image row padded to a whole number of bytes -- `rows` = B*H rows of ceil(W/8) bytes.  The
+ * reference's mask is a torch.bool tensor (1 byte per pixel, loss.py:147); a data loader that ships it packed saves 7/8 of its
+ * host-to-device bytes, which matters because the end-to-end path is bound by exactly those copies. */
+int mgvs_unpack_mask(long long rows, int W, const unsigned char *bits, unsigned char *mask, void *cuda_stream);
 
 /* Self-test hook used by the GPU tests: out[i] = a[i] / b[i] with the library's in-kernel exact division. */
 int mgvs_test_div(const float *a, const float *b, float *out, long long count, void *cuda_stream);

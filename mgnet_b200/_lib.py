@@ -181,6 +181,8 @@ def lib():
     L.mgvs_exchange_bytes.argtypes = []
     L.mgvs_exchange_finalize.restype = ci
     L.mgvs_exchange_finalize.argtypes = [PP, ctypes.POINTER(MgvsPeerExchange), vp, vp, vp]
+    L.mgvs_unpack_mask.restype = ci
+    L.mgvs_unpack_mask.argtypes = [ll, ci, vp, vp, vp]
     L.mgvs_test_div.restype = ci
     L.mgvs_test_div.argtypes = [vp, vp, vp, ll, vp]
     if L.mgvs_abi_version() != ABI_VERSION:
@@ -191,7 +193,7 @@ def lib():
 
 EXPORTED_SYMBOLS = (
     "mgvs_abi_version", "mgvs_last_error", "mgvs_num_sums", "mgvs_workspace_bytes", "mgvs_workspace_bytes_ex", "mgvs_stash_bytes", "mgvs_stash_bytes_ex", "mgvs_forward", "mgvs_forward_diag", "mgvs_forward_losses",
-    "mgvs_finalize", "mgvs_backward", "mgvs_view_synthesis", "mgvs_view_synthesis_ex", "mgvs_reconstruct", "mgvs_project", "mgvs_test_div",
+    "mgvs_finalize", "mgvs_backward", "mgvs_view_synthesis", "mgvs_view_synthesis_ex", "mgvs_reconstruct", "mgvs_project", "mgvs_test_div", "mgvs_unpack_mask",
     "mgvs_dgc_workspace_bytes", "mgvs_dgc_rescale", "mgvs_dgc_heights",
     "mgvs_uncertainty_forward", "mgvs_uncertainty_backward",
     "mgvs_exchange_bytes", "mgvs_exchange_finalize",

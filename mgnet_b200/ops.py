@@ -182,8 +182,16 @@ class _ViewSynthesisLoss(torch.autograd.Function):
         if mask is not None:
             if not mask.is_cuda:
                 raise RuntimeError("reprojection_mask must be on CUDA")
+            if mask.dtype == torch.uint8 and tuple(mask.shape) == (B, 1, H, (W + 7) // 8):
+                # bit-packed mask (numpy.packbits(mask, axis=-1)): 1/8 of the bytes on the host-to-device link; unpacked here
+                bits = mask.contiguous()
+                mask = torch.empty((B, 1, H, W), dtype=torch.bool, device=bits.device)
+                with torch.cuda.device(bits.device):
+                    _lib.check(L.mgvs_unpack_mask(B * H, W, bits.data_ptr(), mask.data_ptr(),
+                                                  ctypes.c_void_p(torch.cuda.current_stream(bits.device).cuda_stream)), "mgvs_unpack_mask")
+                launch_counter.n += 1
             if tuple(mask.shape) != (B, 1, H, W):
-                raise ValueError("reprojection_mask must be [B,1,H,W]")
+                raise ValueError("reprojection_mask must be [B,1,H,W] (bool / integer) or the bit-packed uint8 [B,1,H,ceil(W/8)]")
             if mask.dtype != torch.bool:
                 mask = mask != 0
             mask = mask.contiguous()

@@ -10,7 +10,7 @@ from __future__ import annotations
 import torch
 import torch.nn.functional as F
 
-__all__ = ["make_inputs", "kitti_like_K", "bytes_per_pixel", "snap_pose_trig", "quantize_images"]
+__all__ = ["make_inputs", "kitti_like_K", "bytes_per_pixel", "snap_pose_trig", "quantize_images", "pack_mask"]
 
 
 def _gen(seed: int) -> torch.Generator:
@@ -137,6 +137,13 @@ def quantize_images(targets):
         tu[k] = u
         tf[k] = (u.float() / 255.0).contiguous()
     return tu, tf
+
+
+def pack_mask(mask: torch.Tensor) -> torch.Tensor:
+    """bool [B,1,H,W] -> bit-packed uint8 [B,1,H,ceil(W/8)] (numpy.packbits along the row, most significant bit first): the
+    form ``MultiViewPhotometricLoss`` accepts as ``targets["reprojection_mask"]`` to cut its host-to-device bytes by 8."""
+    import numpy as np
+    return torch.from_numpy(np.packbits(mask.cpu().numpy().astype(bool), axis=-1)).contiguous()
 
 
 def bytes_per_pixel(n: int, S: int = 2, mask: bool = True, fwd_only: bool = False) -> int:

@@ -8,7 +8,7 @@ reference's fixtures by test_gpu_parity / test_gpu_bench_shapes; here it is the 
     warped source equal to the un-warped one);
   * "recheck_all" (every pixel goes through the warp-level exact re-evaluation) must reproduce the exact kernel's sums bit for
     bit -- this pins the re-evaluation machinery itself;
-  * the photometric loss must agree to 1e-6 relative (bar: 1e-5), the gradients to 3e-5 (bar: 1e-4);
+  * the photometric loss must agree to 1e-6 relative (bar: 1e-5), the gradients to 5e-5 (bar: 1e-4; the gated forward writes its stash coefficients from the fast evaluation);
   * the per-pixel error bound must hold with room: max |fast - exact| / bound over EVERY pixel (recheck_all) stays below 1/2.
 """
 import numpy as np
@@ -44,8 +44,8 @@ def _check(r, n, npix, max_recheck_frac=None):
     assert relerr(ga["loss_photometric"], ex["loss_photometric"]) <= 1e-6
     assert ga["loss_smoothness"] == ex["loss_smoothness"]
     for a, b in zip(ga["grad_depth"], ex["grad_depth"]):
-        assert l2rel(a, b) <= 3e-5 and maxrel(a, b) <= 3e-5
-    assert l2rel(ga["grad_poses"], ex["grad_poses"]) <= 3e-5
+        assert l2rel(a, b) <= 5e-5 and maxrel(a, b) <= 5e-5
+    assert l2rel(ga["grad_poses"], ex["grad_poses"]) <= 5e-5
     # the bound: measured on every pixel of every scale
     assert ra["diag"][2] < 0.5, "max |fast - exact| / bound = %.3f" % ra["diag"][2]
     if max_recheck_frac is not None:

@@ -273,3 +273,22 @@ def test_random_configurations_against_oracle(c, backward):
         assert l2rel(r["grad_depth"][i], g["grad_depth"][i]) <= GRAD_RTOL
     if float(np.abs(g["grad_poses"]).max()) > 0:
         assert l2rel(r["grad_poses"], g["grad_poses"]) <= GRAD_RTOL
+
+
+@pytest.mark.parametrize("shape", [(2, 64, 128), (3, 37, 75), (1, 192, 640)])
+def test_bitpacked_mask_matches_bool_mask(shape):
+    """targets["reprojection_mask"] as numpy.packbits bytes (mgvs_unpack_mask): identical results, 1/8 of the mask's H2D bytes."""
+    dev = _dev()
+    from mgnet_b200.synthetic import make_inputs, pack_mask
+    B, H, W = shape
+    pred, tgt = make_inputs(B, H, W, 2, seed=23)
+    hp = dict(ssim_loss_weight=0.85, photometric_loss_weight=1.0, smoothing_loss_weight=1e-3, automask_loss=True,
+              photometric_reduce_op="min", padding_mode="zeros")
+    a = _run_cuda(pred, tgt, hp, dev)
+    packed = dict(tgt, reprojection_mask=pack_mask(tgt["reprojection_mask"]))
+    assert packed["reprojection_mask"].shape == (B, 1, H, (W + 7) // 8) and packed["reprojection_mask"].dtype == torch.uint8
+    b = _run_cuda(pred, packed, hp, dev)
+    assert a["loss_photometric"] == b["loss_photometric"] and a["loss_smoothness"] == b["loss_smoothness"]
+    assert np.array_equal(a["sel"], b["sel"]) and np.array_equal(a["grad_poses"], b["grad_poses"])
+    for x, y in zip(a["grad_depth"], b["grad_depth"]):
+        assert np.array_equal(x, y)
