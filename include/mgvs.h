@@ -24,22 +24,12 @@ extern "C" {
 #endif
 
 #define MGVS_ABI_VERSION 7   /* v2 image_dtype, v3 stash, v4 inv_height/inv_width, v5 padding modes, ssim_weight == 0, DGC, uncertainty, peer exchange,
-                                v6 pose_mats, camera_lift of mgvs_view_synthesis_ex, differentiable geometry ops, pose tail, exchange status,
-                                v7 forward_mode (margin-gated fast SSIM evaluation), mgvs_forward_diag, mgvs_unpack_mask */
+                                v6 pose_mats, camera_lift of mgvs_view_synthesis_ex, exchange status word,
+                                v7 mgvs_unpack_mask (bit-packed reprojection mask), mgvs_pose_tail_* */
 #define MGVS_MAX_SCALES 8   /* n: number of inverse-depth maps (reference: 3, mg_net.py:760-764) */
 #define MGVS_NUM_SOURCES 2  /* S: prev, next -- hard-coded in the reference (loss.py:116) */
 
 enum { MGVS_IMAGE_F32 = 0, MGVS_IMAGE_U8 = 1 };
-
-/* MgvsProblem.forward_mode: how the forward evaluates the per-pixel photometric losses of the warped sources.
- *   MGVS_FORWARD_EXACT (default)  the reference's fp32 rounding sequence at every pixel
- *   MGVS_FORWARD_GATED            separable-sum / FMA-contracted SSIM with a per-pixel error bound; every pixel whose minimum is
- *                                 not separated from the other candidates by more than the bounds is re-evaluated with the exact
- *                                 chain, so `sel` is still bit-exact and the losses agree with the exact evaluation to ~1e-7
- *                                 relative.  Measured SLOWER than EXACT on B200 (the gate costs more than the evaluation saves,
- *                                 DESIGN.md section 5a); kept as a tested option, not the default.
- *   MGVS_FORWARD_RECHECK_ALL      tests only: the gated kernel with every pixel treated as a near-tie (sums bit-identical to EXACT) */
-enum { MGVS_FORWARD_EXACT = 0, MGVS_FORWARD_GATED = 1, MGVS_FORWARD_RECHECK_ALL = 2 };
 
 enum {
     MGVS_OK = 0,
@@ -106,7 +96,6 @@ typedef struct MgvsProblem {
                                    (torch-CPU sin/cos are MKL-VML values, 1 ulp off the correctly rounded ones the kernel uses for ~5 %
                                    of arguments), so the selection mask is bit-exact for ANY angles.  mgvs_backward then writes
                                    grad_poses as [B,S,3,4] = dL/d(R|t) (no Euler chain; autograd of the caller's pose_vec2mat does it). */
-    int forward_mode;           /* MGVS_FORWARD_* (0 = exact, the default) */
 } MgvsProblem;
 
 int mgvs_abi_version(void);
@@ -139,12 +128,6 @@ int mgvs_num_sums(int n);
  *        With ssim_weight == 0 every list entry has 3 channels and the index is entry * 3 + channel (0..11).
  *   sums [3n+3] double out: this rank's partial sums (see above). */
 int mgvs_forward(const MgvsProblem *p, unsigned char *sel, double *sums, void *cuda_stream);
-
-/* Statistics of the last mgvs_forward on this workspace (MGVS_FORWARD_GATED / RECHECK_ALL): *diag_dev receives a DEVICE pointer
- * into p->workspace to three 64-bit words, [0] pixels (summed over scales) that were re-evaluated with the exact chain, [1] how
- * many of those changed their selection, [2] the fp32 bit pattern of max |fast - exact| / bound over the re-evaluated pixels (the
- * bound is sound while this stays below 1).  Valid once the forward's launches have completed; the caller copies them. */
-int mgvs_forward_diag(const MgvsProblem *p, const unsigned long long **diag_dev);
 
 /* Single-rank convenience: mgvs_forward followed by mgvs_finalize in the same launches (the last block of the
  * reduction also writes the two losses).  losses [2] float out; NULL behaves exactly like mgvs_forward. */
@@ -268,6 +251,13 @@ int mgvs_uncertainty_forward(int k, const float *raw, const float *log_vars, con
 /*   g_weighted [k] in;  g_raw [k] = g * tau * exp(-s);  g_log_vars [k] = g * (0.5 - tau * exp(-s) * raw) */
 int mgvs_uncertainty_backward(int k, const float *raw, const float *log_vars, const float *tau_host,
                               const float *g_weighted, float *g_raw, float *g_log_vars, void *cuda_stream);
+
+/* PoseCNN tail (reference layers.py:164-166): out[m] = scale * mean over rows of the row means of map m, for `maps` = B * 6 *
+ * num_context_images contiguous [h, w] fp32 maps (the output of PoseCNN.conv4); scale = 0.01.  `out` viewed as [B, num_context, 6]
+ * is predictions["poses"].  Deterministic (fixed-order fp64 accumulation); replaces three ATen launches forward and three backward
+ * with one each.  backward: gx[m, :, :] = g[m] * scale / (h * w). */
+int mgvs_pose_tail_forward(int maps, int h, int w, const float *x, float scale, float *out, void *cuda_stream);
+int mgvs_pose_tail_backward(int maps, int h, int w, const float *g, float scale, float *gx, void *cuda_stream);
 
 /* Bit-packed reprojection mask -> the byte-per-pixel bool tensor MgvsProblem.mask expects.  `bits` is numpy.packbits(mask, axis=-1):
  * most significant bit first, every image row padded to a whole number of bytes -- `rows` = B*H rows of ceil(W/8) bytes.  The

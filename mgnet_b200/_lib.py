@@ -17,8 +17,6 @@ LIB_PATH = os.environ.get("MGVS_LIB_PATH") or os.path.join(_HERE, "libmgvs.so") 
 MAX_SCALES = 8
 ABI_VERSION = 7
 IMAGE_F32, IMAGE_U8 = 0, 1
-FORWARD_EXACT, FORWARD_GATED, FORWARD_RECHECK_ALL = 0, 1, 2
-FORWARD_MODES = {"gated": FORWARD_GATED, "exact": FORWARD_EXACT, "recheck_all": FORWARD_RECHECK_ALL}
 NUM_SOURCES = 2
 
 NVCC_FLAGS = [
@@ -45,7 +43,6 @@ class MgvsProblem(ctypes.Structure):
         ("stash", ctypes.c_void_p), ("stash_bytes", ctypes.c_size_t),
         ("inv_height", ctypes.c_int * MAX_SCALES), ("inv_width", ctypes.c_int * MAX_SCALES),
         ("pose_mats", ctypes.c_void_p),
-        ("forward_mode", ctypes.c_int),
     ]
 
 
@@ -150,8 +147,6 @@ def lib():
     L.mgvs_stash_bytes_ex.argtypes = [ci, ci, ci, ci, ci]
     L.mgvs_forward.restype = ci
     L.mgvs_forward.argtypes = [PP, vp, vp, vp]
-    L.mgvs_forward_diag.restype = ci
-    L.mgvs_forward_diag.argtypes = [PP, ctypes.POINTER(vp)]
     L.mgvs_forward_losses.restype = ci
     L.mgvs_forward_losses.argtypes = [PP, vp, vp, vp, vp]
     L.mgvs_finalize.restype = ci
@@ -181,6 +176,10 @@ def lib():
     L.mgvs_exchange_bytes.argtypes = []
     L.mgvs_exchange_finalize.restype = ci
     L.mgvs_exchange_finalize.argtypes = [PP, ctypes.POINTER(MgvsPeerExchange), vp, vp, vp]
+    L.mgvs_pose_tail_forward.restype = ci
+    L.mgvs_pose_tail_forward.argtypes = [ci, ci, ci, vp, ctypes.c_float, vp, vp]
+    L.mgvs_pose_tail_backward.restype = ci
+    L.mgvs_pose_tail_backward.argtypes = [ci, ci, ci, vp, ctypes.c_float, vp, vp]
     L.mgvs_unpack_mask.restype = ci
     L.mgvs_unpack_mask.argtypes = [ll, ci, vp, vp, vp]
     L.mgvs_test_div.restype = ci
@@ -192,8 +191,8 @@ def lib():
 
 
 EXPORTED_SYMBOLS = (
-    "mgvs_abi_version", "mgvs_last_error", "mgvs_num_sums", "mgvs_workspace_bytes", "mgvs_workspace_bytes_ex", "mgvs_stash_bytes", "mgvs_stash_bytes_ex", "mgvs_forward", "mgvs_forward_diag", "mgvs_forward_losses",
-    "mgvs_finalize", "mgvs_backward", "mgvs_view_synthesis", "mgvs_view_synthesis_ex", "mgvs_reconstruct", "mgvs_project", "mgvs_test_div", "mgvs_unpack_mask",
+    "mgvs_abi_version", "mgvs_last_error", "mgvs_num_sums", "mgvs_workspace_bytes", "mgvs_workspace_bytes_ex", "mgvs_stash_bytes", "mgvs_stash_bytes_ex", "mgvs_forward", "mgvs_forward_losses",
+    "mgvs_finalize", "mgvs_backward", "mgvs_view_synthesis", "mgvs_view_synthesis_ex", "mgvs_reconstruct", "mgvs_project", "mgvs_test_div", "mgvs_unpack_mask", "mgvs_pose_tail_forward", "mgvs_pose_tail_backward",
     "mgvs_dgc_workspace_bytes", "mgvs_dgc_rescale", "mgvs_dgc_heights",
     "mgvs_uncertainty_forward", "mgvs_uncertainty_backward",
     "mgvs_exchange_bytes", "mgvs_exchange_finalize",

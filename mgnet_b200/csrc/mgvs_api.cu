@@ -652,7 +652,6 @@ static int check_problem(const MgvsProblem* p)
     for (int i = 0; i < p->n; i++)
         if (!p->inv_depth[i]) return fail(MGVS_EINVAL, "null inverse-depth pointer");
     if (p->padding_mode < 0 || p->padding_mode > 2) return fail(MGVS_EINVAL, "padding_mode must be 0 (zeros), 1 (border) or 2 (reflection)");
-    if (p->forward_mode < 0 || p->forward_mode > 2) return fail(MGVS_EINVAL, "forward_mode must be MGVS_FORWARD_GATED, _EXACT or _RECHECK_ALL");
     if (p->reduce_op != 0) return fail(MGVS_EUNSUPPORTED, "photometric_reduce_op: the kernels implement 'min'; 'mean' is composed from two 'min' evaluations by the caller (mgnet_b200/loss.py)");
     if (!(p->ssim_weight >= 0.f)) return fail(MGVS_EINVAL, "ssim_loss_weight must be >= 0");
     if (!(p->ssim_weight > 0.f) && lowres_mode(p) != 0) return fail(MGVS_EUNSUPPORTED, "fused upsample with ssim_loss_weight == 0 (it needs the coefficient stash, which the L1-only branch does not have)");
@@ -884,6 +883,32 @@ __global__ void __launch_bounds__(256) unpack_mask_kernel(long long rows, int W,
     }
 }
 
+// ---- PoseCNN tail (reference layers.py:164-166): out[b, c] = 0.01 * mean_h(mean_w(x[b, c, h, w])) -----------------------------
+// One CTA per (b, c) map.  Rows are summed in fp64 in a fixed order (thread t takes rows t, t+128, ...; left to right inside a row),
+// the row means are folded by a fixed shuffle / shared-memory tree: deterministic, and within 1 ulp of the exactly rounded result
+// (ATen's own CPU and CUDA reductions differ from each other in the last bits; this op feeds the pose, not a bit-exact contract).
+__global__ void __launch_bounds__(128) pose_tail_fwd_kernel(int h, int w, const float* __restrict__ x, float scale, float* __restrict__ out)
+{
+    __shared__ double s_part[4];
+    const float* map = x + (size_t)blockIdx.x * h * w;
+    double acc = 0.0;
+    for (int r = threadIdx.x; r < h; r += 128) {
+        double row = 0.0;
+        for (int j = 0; j < w; j++) row += (double)__ldg(map + (size_t)r * w + j);
+        acc += row / (double)w;                       // mean(3)
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if ((threadIdx.x & 31) == 0) s_part[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) out[blockIdx.x] = (float)((double)scale * (((s_part[0] + s_part[1]) + (s_part[2] + s_part[3])) / (double)h));   // mean(2) * 0.01
+}
+__global__ void __launch_bounds__(256) pose_tail_bwd_kernel(long long total, int hw, const float* __restrict__ g, float scale, float* __restrict__ gx)
+{
+    for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < total; i += (long long)gridDim.x * 256)
+        gx[i] = (float)((double)__ldg(g + i / hw) * (double)scale / (double)hw);
+}
+
 extern "C" {
 
 int mgvs_abi_version(void) { return MGVS_ABI_VERSION; }
@@ -963,21 +988,16 @@ int mgvs_forward_losses(const MgvsProblem* p_in, unsigned char* sel, double* sum
         fp.inv_rx[i] = p->W > 1 ? (float)((double)(p->inv_width[i] - 1) / (double)(p->W - 1)) : 0.f;
     }
     fp.early_wait = u8 ? 1 : 0;
-    fp.flag_all = p->forward_mode == MGVS_FORWARD_RECHECK_ALL;
-    fp.diag = (unsigned long long*)(ws + L.counter + 64);
     if (!use_tma) memset(&maps, 0, sizeof(maps));
     fp.stash = (float4*)p->stash; fp.Wg = (p->W + 3) / 4;
     fp.wgt = p->stash ? (float*)((char*)p->stash + stash_texel_bytes(p->B, p->H, p->W, p->n)) : nullptr;
     {
-        // padding_mode "zeros" runs the PAD = false instantiations (unchanged code); "border" / "reflection" the PAD = true ones.
-        // forward_mode EXACT (default): the exact chain everywhere; GATED / RECHECK_ALL: margin-gated fast SSIM evaluation with exact
-        // re-evaluation of near-ties (measured slower)
-        #define MGVS_FWD_PICK(FAST) (p->padding_mode == 0 ? (use_tma ? (p->stash ? fwd_kernel<true, true, false, false, FAST> : fwd_kernel<true, false, false, false, FAST>) \
-                                                                      : (p->stash ? fwd_kernel<false, true, false, false, FAST> : fwd_kernel<false, false, false, false, FAST>)) \
-                                                           : (use_tma ? (p->stash ? fwd_kernel<true, true, true, false, FAST> : fwd_kernel<true, false, true, false, FAST>) \
-                                                                      : (p->stash ? fwd_kernel<false, true, true, false, FAST> : fwd_kernel<false, false, true, false, FAST>)))
-        void (*kern)(FwdParams, FwdMaps) = p->forward_mode == MGVS_FORWARD_EXACT ? MGVS_FWD_PICK(false) : MGVS_FWD_PICK(true);
-        #undef MGVS_FWD_PICK
+        // padding_mode "zeros" runs the PAD = false instantiations (unchanged code); "border" / "reflection" the PAD = true ones
+        void (*kern)(FwdParams, FwdMaps) =
+            p->padding_mode == 0 ? (use_tma ? (p->stash ? fwd_kernel<true, true> : fwd_kernel<true, false>)
+                                            : (p->stash ? fwd_kernel<false, true> : fwd_kernel<false, false>))
+                                 : (use_tma ? (p->stash ? fwd_kernel<true, true, true> : fwd_kernel<true, false, true>)
+                                            : (p->stash ? fwd_kernel<false, true, true> : fwd_kernel<false, false, true>));
         if (l1only)   // ssim_loss_weight == 0: raw 3-channel L1, 12-way min (loss.py:195-196); never with the stash
             kern = p->padding_mode == 0 ? (use_tma ? fwd_kernel<true, false, false, true> : fwd_kernel<false, false, false, true>)
                                         : (use_tma ? fwd_kernel<true, false, true, true> : fwd_kernel<false, false, true, true>);
@@ -993,16 +1013,6 @@ int mgvs_forward_losses(const MgvsProblem* p_in, unsigned char* sel, double* sum
 int mgvs_forward(const MgvsProblem* p, unsigned char* sel, double* sums, void* cuda_stream)
 {
     return mgvs_forward_losses(p, sel, sums, nullptr, cuda_stream);
-}
-
-int mgvs_forward_diag(const MgvsProblem* p, const unsigned long long** diag_dev)
-{
-    int rc = check_problem(p);
-    if (rc) return rc;
-    if (!diag_dev) return fail(MGVS_EINVAL, "null diag_dev");
-    Layout L = make_layout(p->B, p->H, p->W, p->n, p->image_dtype);
-    *diag_dev = (const unsigned long long*)((const char*)p->workspace + L.counter + 64);
-    return MGVS_OK;
 }
 
 int mgvs_finalize(const MgvsProblem* p, const double* sums, float* losses, void* cuda_stream)
@@ -1248,6 +1258,22 @@ int mgvs_exchange_finalize(const MgvsProblem* p, const MgvsPeerExchange* x, doub
     }
     exchange_finalize_kernel<<<1, 256, 0, (cudaStream_t)cuda_stream>>>(p->n, x->rank, x->world, pp, sums, p->photometric_weight, p->smoothing_weight, losses);
     return check_launch("mgvs_exchange_finalize");
+}
+
+int mgvs_pose_tail_forward(int maps, int h, int w, const float* x, float scale, float* out, void* cuda_stream)
+{
+    if (maps < 1 || h < 1 || w < 1 || !x || !out) return fail(MGVS_EINVAL, "bad argument");
+    pose_tail_fwd_kernel<<<maps, 128, 0, (cudaStream_t)cuda_stream>>>(h, w, x, scale, out);
+    return check_launch("mgvs_pose_tail_forward");
+}
+
+int mgvs_pose_tail_backward(int maps, int h, int w, const float* g, float scale, float* gx, void* cuda_stream)
+{
+    if (maps < 1 || h < 1 || w < 1 || !g || !gx) return fail(MGVS_EINVAL, "bad argument");
+    const long long total = (long long)maps * h * w;
+    const int blocks = (int)((total + 255) / 256 < 148 * 8 ? (total + 255) / 256 : 148 * 8);
+    pose_tail_bwd_kernel<<<blocks, 256, 0, (cudaStream_t)cuda_stream>>>(total, h * w, g, scale, gx);
+    return check_launch("mgvs_pose_tail_backward");
 }
 
 int mgvs_unpack_mask(long long rows, int W, const unsigned char* bits, unsigned char* mask, void* cuda_stream)

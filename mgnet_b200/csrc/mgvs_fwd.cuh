@@ -32,8 +32,6 @@ struct FwdParams {
     int inv_h[MAXN], inv_w[MAXN];
     float inv_ry[MAXN], inv_rx[MAXN];
     double* partials;            // [tiles][4n+3]
-    int flag_all;                // FAST kernels, tests only: treat every pixel as a near-tie (everything goes through the exact re-evaluation)
-    unsigned long long* diag;    // FAST kernels: [0] pixels re-evaluated exactly, [1] of those, pixels whose selection changed, [2] bits of max |fast-exact|/bound (integer atomics)
     float alpha, oma;
     int tiles_x, tiles_y;
 };
@@ -143,151 +141,7 @@ __device__ __forceinline__ void photometric4(const float* __restrict__ xs, const
         out[k] = __fadd_rn(__fmul_rn(alpha, exact::div3(ssum[k])), __fmul_rn(oma, exact::div3(lsum[k])));
 }
 
-// ---- margin-gated fast path (north_star: bit-exact SELECTION, 1e-5 on the loss -- not bit-exact per-pixel losses) -----------
-// MEASURED (round 2, profiles/r02e_forward_modes.txt, C2 / C4 forward through the C ABI): exact 0.346 / 2.803 ms; fast evaluation with
-// NO gate (wrong at near-ties, the upper bound of what this can win) 0.326 / 2.622 ms (-6 %: the SSIM stage is co-limited by
-// shared-memory wavefronts, which the fast evaluation does not reduce); with the gate 0.390 / 3.088 ms (+13 %): 0.52 % of C2's
-// pixels are near-ties under the rigorous bound (81 of them would have been mis-selected), and bound + comparison + the exact
-// re-evaluation cost more than the evaluation saves.  Not the default (MGVS_FORWARD_EXACT is); kept as a tested option.
-// photometric4_fast evaluates the same loss with separable window sums (3 column sums shared by the 4 outputs of a strip, FMA
-// contraction, one MUFU.RCP per SSIM) in roughly half the FP32 instructions of the exact row-major chain, and returns with
-// every value a bound eps on |fast - exact|.  The caller compares the candidates of the per-pixel minimum: where the winner is
-// separated from every other candidate by more than the two bounds, the fast selection IS the exact one; the remaining
-// near-ties (a fraction of a percent) are re-evaluated with the exact chain (photometric_pair_exact_warp), so `sel` stays bit-exact.
-//
-// Bound, u = 2^-24, images non-negative.  A 9-term sum of non-negative terms has relative error <= 8u in any
-// order, so in either evaluation: mu_x (1 +- 10u), E[xx] (1 +- 11u), mu_x^2 (1 +- 21u), hence |d sigma_x| <= 32u E[xx] + u sigma_x,
-// |d d2| <= 32u E[xx] + 3u d2, |d d1| <= 23u d1, |d n1| <= 12u n1, |d n2| <= 22u (E[xx] + E[yy]) + 2u |n2| (mu_y, sigma_y are the same
-// numbers in both evaluations and drop out of the difference).  With n1 <= d1, |n2| <= d2 (AM-GM, Cauchy-Schwarz) and
-// E[xx] + E[yy] <= d1 + d2:   |d ssim| <= 42u + 54u (E[xx] + E[yy]) / d2 <= 96u + 54u d1/d2   per evaluation, so
-//   |ssim_fast - ssim_exact| <= 192u + 108u d1/d2 = 192u + 108u d1^2 r,   r = 1/(d1 d2),
-// and through (1 - ssim)/2, the channel mean and alpha:  eps = alpha (96u + 18u sum_c d1^2 r) + 6u; the code uses 100u, 20u, 8u.
-// The L1 term is computed by the same instructions in both paths (no contribution).
-namespace fast {
-constexpr float INV9 = 0.111111111938953399658203125f;
-constexpr float TWO9 = 0.22222222387790679931640625f;
-constexpr float U = 5.9604644775390625e-8f;          // 2^-24
-constexpr float EPS_K = 20.f * U;                    // per unit of sum_c d1/d2, times alpha
-constexpr float EPS_A = 100.f * U;                   // times alpha
-constexpr float EPS_0 = 8.f * U;
-__device__ __forceinline__ float rcp_approx(float x)
-{
-    float y;
-    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-    return y;
-}
-}  // namespace fast
-
-// Same contract as photometric4 plus: eps[k] bounds |out[k] - exact|, bit k of zero_mask = the 3x3x3 window of output k is
-// all zeros (two such windows give bit-identical losses in the exact chain as well: an exact tie, not a near-tie).
-template <bool KEEP, typename Emit>
-__device__ __forceinline__ void photometric4_fast(const float* __restrict__ xs, const float* __restrict__ ys,
-                                                  const float* __restrict__ yst, float alpha, float oma, float out[4],
-                                                  float eps[4], unsigned& zero_mask, Emit emit)
-{
-    const float c1 = 1e-4f, c2 = 9e-4f;
-    float ssum[4], lsum[4], esum[4], zsum[4];
-#pragma unroll
-    for (int ch = 0; ch < 3; ch++) {
-        float cx[6], cxx[6], cxy[6], l1[4];
-#pragma unroll
-        for (int dy = 0; dy < 3; dy++) {
-            const float* xr = xs + ch * FWD_CH + dy * PITCH;
-            const float* yr = ys + ch * FWD_CH + dy * PITCH;
-            float4 xm = *reinterpret_cast<const float4*>(xr), ym = *reinterpret_cast<const float4*>(yr);
-            float x6[6] = {xr[-1], xm.x, xm.y, xm.z, xm.w, xr[4]};
-            float y6[6] = {yr[-1], ym.x, ym.y, ym.z, ym.w, yr[4]};
-#pragma unroll
-            for (int j = 0; j < 6; j++) {
-                if (dy == 0) { cx[j] = x6[j]; cxx[j] = x6[j] * x6[j]; cxy[j] = x6[j] * y6[j]; }
-                else { cx[j] += x6[j]; cxx[j] = fmaf(x6[j], x6[j], cxx[j]); cxy[j] = fmaf(x6[j], y6[j], cxy[j]); }
-            }
-            if (dy == 1) {
-#pragma unroll
-                for (int k = 0; k < 4; k++) l1[k] = fabsf(__fadd_rn(x6[k + 1], -y6[k + 1]));     // same instruction as the exact chain
-            }
-        }
-        float4 muy = *reinterpret_cast<const float4*>(yst + (ch * 2 + 0) * TH * TW);
-        float4 sgy = *reinterpret_cast<const float4*>(yst + (ch * 2 + 1) * TH * TW);
-        const float muy4[4] = {muy.x, muy.y, muy.z, muy.w}, sgy4[4] = {sgy.x, sgy.y, sgy.z, sgy.w};
-#pragma unroll
-        for (int k = 0; k < 4; k++) {
-            const float sx = (cx[k] + cx[k + 1]) + cx[k + 2];
-            const float sxx = (cxx[k] + cxx[k + 1]) + cxx[k + 2];
-            const float sxy = (cxy[k] + cxy[k + 1]) + cxy[k + 2];
-            const float mu_y = muy4[k];
-            const float A = fmaf(mu_y, mu_y, c1), Bq = sgy4[k] + c2;
-            const float mu_x = sx * fast::INV9;
-            const float t = mu_x * mu_y;
-            const float n1 = fmaf(2.f, t, c1);
-            const float n2 = fmaf(-2.f, t, fmaf(sxy, fast::TWO9, c2));
-            const float mxs = mu_x * mu_x;
-            const float d1 = mxs + A;
-            const float d2 = fmaf(sxx, fast::INV9, -mxs) + Bq;
-            const float r = fast::rcp_approx(d1 * d2);
-            const float ssim = (n1 * n2) * r;
-            const float lraw = fmaf(-0.5f, ssim, 0.5f);
-            const float l = __saturatef(lraw);
-            const float eb = (d1 * d1) * r;              // d1 / d2
-            if (KEEP) {
-                // same closed form as the exact path (see photometric4): e = 2/(d1 d2), zero where the clamp is inactive
-                const bool ok = lraw >= 0.f && lraw <= 1.f;
-                const float e = ok ? r + r : 0.f;
-                const float sm = ssim * mu_x;
-                emit(ch, k, e * fmaf(mu_y, n2 - n1, -sm * (d2 - d1)), -e * (ssim * d1), e * n1);
-            }
-            if (ch == 0) { ssum[k] = l; lsum[k] = l1[k]; esum[k] = eb; zsum[k] = sxx; }
-            else { ssum[k] += l; lsum[k] = __fadd_rn(lsum[k], l1[k]); esum[k] += eb; zsum[k] += sxx; }
-        }
-    }
-    zero_mask = 0;
-#pragma unroll
-    for (int k = 0; k < 4; k++) {
-        out[k] = fmaf(alpha * (1.f / 3.f), ssum[k], __fmul_rn(oma, exact::div3(lsum[k])));
-        eps[k] = fmaf(esum[k], alpha * fast::EPS_K, fmaf(alpha, fast::EPS_A, fast::EPS_0));
-        zero_mask |= (zsum[k] == 0.f ? 1u : 0u) << k;
-    }
-}
-
-// Exact photometric losses of ONE output against both warped sources, evaluated by a whole warp: lane l < 18 runs one of the 18
-// row-major 9-term chains (source l/9, channel (l%9)/3, quantity l%3 in {x, x*x, x*y}) -- each chain has the operation order of
-// photometric4, so the sums carry the same bits -- lanes 0..5 then turn the sums of their (source, channel) into the SSIM term and
-// lanes 0 and 3 fold the channels.  All lanes return both losses.  x0, x1, ys: [ch 0][halo row of the output's row - 1][column of the output - 1]
-// (the top-left tap of its 3x3 window); yst1: target statistics of the output.
-__device__ __forceinline__ void photometric_pair_exact_warp(const float* __restrict__ x0, const float* __restrict__ x1,
-                                                            const float* __restrict__ ys, const float* __restrict__ yst1, float alpha,
-                                                            float oma, int lane, float& out0, float& out1)
-{
-    const int l18 = lane < 18 ? lane : 0;
-    const int s = l18 / 9, ch = (l18 % 9) / 3, q = l18 % 3;
-    const float* xs = (s == 0 ? x0 : x1) + ch * FWD_CH;
-    const float* yc = ys + ch * FWD_CH;
-    float acc = 0.f;
-#pragma unroll
-    for (int dy = 0; dy < 3; dy++)
-#pragma unroll
-        for (int j = 0; j < 3; j++) {
-            const float x = xs[dy * PITCH + j];
-            const float v = q == 0 ? x : __fmul_rn(x, q == 1 ? x : yc[dy * PITCH + j]);
-            acc = (dy == 0 && j == 0) ? v : __fadd_rn(acc, v);
-        }
-    // lanes 0..5: (source, channel) = (lane / 3, lane % 3); their three sums sit in lanes 9 s + 3 ch + {0, 1, 2}
-    const int l6 = lane < 6 ? lane : 0;
-    const int s6 = l6 / 3, c6 = l6 % 3, src = 9 * s6 + 3 * c6;
-    const float sx = __shfl_sync(0xffffffffu, acc, src), sxx = __shfl_sync(0xffffffffu, acc, src + 1), sxy = __shfl_sync(0xffffffffu, acc, src + 2);
-    const float muy = yst1[(c6 * 2 + 0) * TH * TW], sgy = yst1[(c6 * 2 + 1) * TH * TW];
-    const float l = exact::ssim_from_sums(sx, sxx, sxy, muy, __fmul_rn(muy, muy), sgy, nullptr);
-    const float l1 = fabsf(__fadd_rn((s6 == 0 ? x0 : x1)[c6 * FWD_CH + PITCH + 1], -ys[c6 * FWD_CH + PITCH + 1]));
-    // lanes 0 and 3: ((c0 + c1) + c2) of their source
-    const float la = __shfl_down_sync(0xffffffffu, l, 1), lb = __shfl_down_sync(0xffffffffu, l, 2);
-    const float ma = __shfl_down_sync(0xffffffffu, l1, 1), mb = __shfl_down_sync(0xffffffffu, l1, 2);
-    const float ssum = __fadd_rn(__fadd_rn(l, la), lb), lsum = __fadd_rn(__fadd_rn(l1, ma), mb);
-    const float r = __fadd_rn(__fmul_rn(alpha, exact::div3(ssum)), __fmul_rn(oma, exact::div3(lsum)));
-    out0 = __shfl_sync(0xffffffffu, r, 0);
-    out1 = __shfl_sync(0xffffffffu, r, 3);
-}
-
-template <bool USE_TMA, bool STASH, bool PAD = false, bool L1ONLY = false, bool FAST = false>
+template <bool USE_TMA, bool STASH, bool PAD = false, bool L1ONLY = false>
 __global__ void __launch_bounds__(NT, MIN_CTAS) fwd_kernel(const FwdParams p, const __grid_constant__ FwdMaps maps)
 {
     extern __shared__ __align__(128) float smem[];
@@ -525,104 +379,42 @@ __global__ void __launch_bounds__(NT, MIN_CTAS) fwd_kernel(const FwdParams p, co
         float c1[3][3][4];
         // rows below the image and column groups right of it do not exist in the stash (the backward's TMA zero-fills them)
         const bool row_ok = STASH && v < H && (x0 >> 2) + tx < p.Wg;
-        if (STASH) st = p.stash + ((size_t)i * p.B + b) * 3 * st_ch + (size_t)v * 4 * p.Wg + (x0 >> 2) + tx;
-        const float* xs0_t = sX + ty * PITCH + XOFF + 4 * tx;
-        const float* xs1_t = sX + FWD_TILE3_FLOATS + ty * PITCH + XOFF + 4 * tx;
-        auto emit0 = [&](int ch, int k, float a, float bq, float c) {
-            if (row_ok) __stcs(st + ch * st_ch + k * p.Wg, make_float4(a, bq, c, 1.f));     // streaming: written once, read once
-        };
-        auto emit1 = [&](int ch, int k, float a, float bq, float c) { c1[ch][0][k] = a; c1[ch][1][k] = bq; c1[ch][2][k] = c; };
 #if MGVS_ABL & 2
-        for (int k = 0; k < 4; k++) { lw0[k] = xs0_t[k]; lw1[k] = xs1_t[k]; }
+        for (int k = 0; k < 4; k++) { lw0[k] = sX[ty * PITCH + XOFF + 4 * tx + k]; lw1[k] = sX[FWD_TILE3_FLOATS + ty * PITCH + XOFF + 4 * tx + k]; }
         for (int ch = 0; ch < 3; ch++) for (int m = 0; m < 3; m++) for (int k = 0; k < 4; k++) c1[ch][m][k] = lw1[k];
+        if (STASH) st = p.stash + ((size_t)i * p.B + b) * 3 * st_ch + (size_t)v * 4 * p.Wg + (x0 >> 2) + tx;
+        if (false) {
 #else
-        if constexpr (L1ONLY) {
-        } else if constexpr (FAST) {
-            // ---- margin-gated fast evaluation (see photometric4_fast) ----
-            float e0[4], e1[4];
-            unsigned z0, z1;
-            if constexpr (STASH) {
-                photometric4_fast<true>(xs0_t, ys_t, yst_t, p.alpha, p.oma, lw0, e0, z0, emit0);
-                photometric4_fast<true>(xs1_t, ys_t, yst_t, p.alpha, p.oma, lw1, e1, z1, emit1);
-            } else {
-                photometric4_fast<false>(xs0_t, ys_t, yst_t, p.alpha, p.oma, lw0, e0, z0, NoEmit());
-                photometric4_fast<false>(xs1_t, ys_t, yst_t, p.alpha, p.oma, lw1, e1, z1, NoEmit());
-            }
-            // near-ties: the fast winner is the exact winner unless another candidate lies within the two error bounds of it
-            // (two all-zero windows are an exact tie in both evaluations: lowest index, no re-evaluation needed)
-            unsigned flags = 0, fastsel = 0;
-#pragma unroll
-            for (int k = 0; k < 4; k++) {
-                const float a0 = lw0[k], a1 = lw1[k], ai = lid0[k];
-                const bool zz = ((z0 & z1) >> k) & 1u;
-                int bs = 0;                      // slot of the fast winner: 0 warp_prev, 1 identity, 2 warp_next
-                float best = a0;
-                if (p.automask && ai < best) { best = ai; bs = 1; }
-                if (a1 < best) { best = a1; bs = 2; }
-                const float eb = bs == 0 ? e0[k] : (bs == 2 ? e1[k] : 0.f);
-                bool amb = false;
-                if (bs != 0) amb = amb || ((a0 - best <= e0[k] + eb) && !(bs == 2 && zz));
-                if (bs != 2) amb = amb || ((a1 - best <= e1[k] + eb) && !(bs == 0 && zz));
-                if (p.automask && bs != 1) amb = amb || (ai - best <= eb);
-#if !(MGVS_ABL & 16)      // (ablation 16: no gating at all -- the price of the fast evaluation alone; WRONG selection at near-ties)
-                if ((amb || p.flag_all) && valid[k]) flags |= 1u << k;
+        if (STASH) {
 #endif
-                fastsel |= (unsigned)bs << (2 * k);
-            }
-            // warp-level re-evaluation: the flagged (lane, k) pixels of the warp are visited one by one, the whole warp working on
-            // ONE pixel (photometric_pair_exact_warp: ~110 warp-instructions per pixel instead of ~660 for a one-lane evaluation);
-            // warp-uniform control flow, no extra block barrier
-            unsigned mk[4];
-#pragma unroll
-            for (int k = 0; k < 4; k++) mk[k] = __ballot_sync(0xffffffffu, (flags >> k) & 1u);
-            const int total = __popc(mk[0]) + __popc(mk[1]) + __popc(mk[2]) + __popc(mk[3]);
-            if (total != 0) {                    // warp-uniform
-                const float f0[4] = {lw0[0], lw0[1], lw0[2], lw0[3]}, f1[4] = {lw1[0], lw1[1], lw1[2], lw1[3]};     // for the statistics below
+            st = p.stash + ((size_t)i * p.B + b) * 3 * st_ch + (size_t)v * 4 * p.Wg + (x0 >> 2) + tx;
+#if MGVS_ROLL_SRC
 #pragma unroll 1
-                for (int k = 0; k < 4; k++) {     // a real loop: one copy of the evaluator in the instruction stream
-                    for (unsigned rem = k == 0 ? mk[0] : (k == 1 ? mk[1] : (k == 2 ? mk[2] : mk[3])); rem != 0; rem &= rem - 1) {
-                        const int owner = __ffs(rem) - 1;
-                        const int otid = (tid & ~31) + owner;
-                        const int oty = otid / CG, col = 4 * (otid % CG) + k;
-                        const int o = oty * PITCH + XOFF + col - 1;
-                        float x0e, x1e;
-                        photometric_pair_exact_warp(sX + o, sX + FWD_TILE3_FLOATS + o, sY + o, sYst + oty * TW + col, p.alpha, p.oma, lane, x0e, x1e);
-                        if (lane == owner) {
+            for (int s = 0; s < 2; s++) {
+                float lw[4];
+                photometric4<true>(sX + s * FWD_TILE3_FLOATS + ty * PITCH + XOFF + 4 * tx, ys_t, yst_t, p.alpha, p.oma, lw,
+                                   [&](int ch, int k, float a, float bq, float c) {
+                                       if (s == 0) { if (row_ok) __stcs(st + ch * st_ch + k * p.Wg, make_float4(a, bq, c, 1.f)); }
+                                       else { c1[ch][0][k] = a; c1[ch][1][k] = bq; c1[ch][2][k] = c; }
+                                   });
 #pragma unroll
-                            for (int kk = 0; kk < 4; kk++) if (kk == k) { lw0[kk] = x0e; lw1[kk] = x1e; }
-                        }
-                    }
-                }
-                if (p.diag != nullptr) {
-                    // statistics only (integer atomics: deterministic): pixels re-evaluated, and how many of them changed their selection
-                    int changed = 0;
-                    float ratio = 0.f;           // max |fast - exact| / bound over the re-evaluated pixels: must stay well below 1
-#pragma unroll
-                    for (int k = 0; k < 4; k++) {
-                        if (!((flags >> k) & 1u)) continue;
-                        ratio = fmaxf(ratio, fmaxf(fabsf(f0[k] - lw0[k]) / e0[k], fabsf(f1[k] - lw1[k]) / e1[k]));
-                        int bs = 0;
-                        float best = lw0[k];
-                        if (p.automask && lid0[k] < best) { best = lid0[k]; bs = 1; }
-                        if (lw1[k] < best) bs = 2;
-                        changed += bs != (int)((fastsel >> (2 * k)) & 3u);
-                    }
-                    changed = __reduce_add_sync(0xffffffffu, changed);
-                    const unsigned rbits = __reduce_max_sync(0xffffffffu, __float_as_uint(ratio));     // non-negative floats order like their bits
-                    if (lane == 0) {
-                        atomicAdd(p.diag, (unsigned long long)total); atomicAdd(p.diag + 1, (unsigned long long)changed);
-                        atomicMax(p.diag + 2, (unsigned long long)rbits);
-                    }
-                }
+                for (int k = 0; k < 4; k++) { if (s == 0) lw0[k] = lw[k]; else lw1[k] = lw[k]; }
             }
-        } else if constexpr (STASH) {
-            photometric4<true>(xs0_t, ys_t, yst_t, p.alpha, p.oma, lw0, emit0);
-            photometric4<true>(xs1_t, ys_t, yst_t, p.alpha, p.oma, lw1, emit1);
-        } else {
-            photometric4<false>(xs0_t, ys_t, yst_t, p.alpha, p.oma, lw0, NoEmit());
-            photometric4<false>(xs1_t, ys_t, yst_t, p.alpha, p.oma, lw1, NoEmit());
-        }
+            if (false)
 #endif
+            photometric4<true>(sX + ty * PITCH + XOFF + 4 * tx, ys_t, yst_t, p.alpha, p.oma, lw0,
+                               [&](int ch, int k, float a, float bq, float c) {
+                                   if (row_ok) __stcs(st + ch * st_ch + k * p.Wg, make_float4(a, bq, c, 1.f));     // streaming: written once, read once
+                               });
+#if MGVS_ROLL_SRC
+            if (false)
+#endif
+            photometric4<true>(sX + FWD_TILE3_FLOATS + ty * PITCH + XOFF + 4 * tx, ys_t, yst_t, p.alpha, p.oma, lw1,
+                               [&](int ch, int k, float a, float bq, float c) { c1[ch][0][k] = a; c1[ch][1][k] = bq; c1[ch][2][k] = c; });
+        } else if constexpr (!L1ONLY && !(MGVS_ABL & 2)) {
+            photometric4<false>(sX + ty * PITCH + XOFF + 4 * tx, ys_t, yst_t, p.alpha, p.oma, lw0, NoEmit());
+            photometric4<false>(sX + FWD_TILE3_FLOATS + ty * PITCH + XOFF + 4 * tx, ys_t, yst_t, p.alpha, p.oma, lw1, NoEmit());
+        }
         float photo = 0.f;
         unsigned selw = 0;
 #pragma unroll

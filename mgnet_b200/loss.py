@@ -32,7 +32,6 @@ class MultiViewPhotometricLoss(nn.Module):
         ddp_grad_scale=False,
         backward="stash",
         fuse_upsample=False,
-        forward_mode="exact",
     ):
         super().__init__()
         self.n = None
@@ -48,7 +47,6 @@ class MultiViewPhotometricLoss(nn.Module):
             raise ValueError("exchange= needs process_group=")
         self.ddp_grad_scale = ddp_grad_scale
         self.fuse_upsample = fuse_upsample   # predictions["depth"] are the head's low-resolution maps; see ops.LossConfig
-        self.forward_mode = forward_mode     # "exact" or "gated" (fast SSIM evaluation, exact re-evaluation of near-ties; slower), see ops.LossConfig
         self.backward = backward     # "stash" (fast, +48 B/px/scale of scratch) or "recompute" (lean memory), see ops.LossConfig
         self.last_selection = None   # uint8 [n,B,H,W] argmin of the most recent forward (new side output)
         # same assertion as the reference (loss.py:106-109)
@@ -84,8 +82,6 @@ class MultiViewPhotometricLoss(nn.Module):
             ddp_grad_scale=bool(self.ddp_grad_scale),
             backward=self.backward,
             fuse_upsample=bool(self.fuse_upsample),
-            forward_mode=self.forward_mode,
-            collect_diag=bool(getattr(self, "collect_diag", False)),
         )
 
     def forward(self, predictions, targets):
@@ -200,8 +196,7 @@ class MultiViewPhotometricLoss(nn.Module):
         (identical maps tie, the strict `<` scan keeps index 0, so slot 0 carries the whole gradient).  The smoothness term does
         not depend on the sources and is taken from the first evaluation."""
         import dataclasses
-        # (both slots hold the same frame: every pixel is an exact tie, which a gated forward would re-evaluate one by one)
-        cfg = dataclasses.replace(self._config(), photometric_reduce_op="min", automask_loss=False, forward_mode="exact")
+        cfg = dataclasses.replace(self._config(), photometric_reduce_op="min", automask_loss=False)
         inv = [d.float() for d in predictions["depth"]]
         poses = predictions["poses"].float()
         if poses.dim() == 4:

@@ -23,7 +23,6 @@ class _Counter:
 
 
 launch_counter = _Counter()
-last_forward_diag = None   # (pixels re-evaluated, selections changed, max |fast - exact| / bound) of the latest forward run with collect_diag
 FWD_LAUNCHES = 3   # pack_sources_kernel (+camera table), fwd_kernel, reduce_kernel
 FIN_LAUNCHES = 1   # finalize_kernel
 BWD_LAUNCHES = 2   # bwd_kernel, pose_reduce_kernel
@@ -48,13 +47,6 @@ class LossConfig:
                                       # mode="bilinear", align_corners=True), mg_net.py:803-806,823); the kernels upsample on
                                       # the fly (bit-identical to ATen's CPU kernel) and return low-resolution gradients
                                       # through a deterministic adjoint.  Needs backward="stash".
-    forward_mode: str = "exact"       # "exact" (default): the reference's fp32 rounding sequence at every pixel; "gated": SSIM with
-                                      # separable, FMA-contracted window sums and a per-pixel error bound, exact re-evaluation only of
-                                      # the pixels whose minimum is not separated by more than the bound (selection still bit-exact,
-                                      # losses within ~1e-7) -- measured slower on B200, kept as a tested option;
-                                      # "recheck_all": tests only (include/mgvs.h MGVS_FORWARD_*)
-    collect_diag: bool = False        # tests / bench: after the forward, read the gated path's statistics into ops.last_forward_diag
-                                      # (synchronises the device)
     backward: str = "stash"           # "stash": the forward also writes the SSIM-adjoint coefficient texels of the
                                       # selected source (48 B/px/scale) and the backward consumes them (fastest);
                                       # "recompute": nothing but the uint8 selection is carried over and the backward
@@ -112,9 +104,6 @@ def _fill_problem(prob, cfg, tgt, prev, nxt, inv, camera, poses, mask, ws, stash
     prob.automask = int(bool(cfg.automask_loss))
     prob.reduce_op = 0
     prob.padding_mode = _lib.PADDING_MODES[cfg.padding_mode]
-    if cfg.forward_mode not in _lib.FORWARD_MODES:
-        raise ValueError("forward_mode must be one of %s, got %r" % (sorted(_lib.FORWARD_MODES), cfg.forward_mode))
-    prob.forward_mode = _lib.FORWARD_MODES[cfg.forward_mode]
     prob.workspace = ws.data_ptr()
     prob.workspace_bytes = ws.numel()
     prob.stash = stash.data_ptr() if stash is not None else None
@@ -123,17 +112,6 @@ def _fill_problem(prob, cfg, tgt, prev, nxt, inv, camera, poses, mask, ws, stash
         lowres = tuple(d.shape[-2:]) != (H, W)
         prob.inv_height[i] = d.shape[-2] if lowres else 0
         prob.inv_width[i] = d.shape[-1] if lowres else 0
-
-
-def forward_diag(prob, ws: torch.Tensor):
-    """(pixels re-evaluated with the exact chain, of those: selections that changed, max |fast - exact| / bound over them) of the
-    last gated forward on workspace `ws` (mgvs_forward_diag).  Synchronises (one 24-byte device-to-host copy): statistics for
-    tests and the bench, not the step."""
-    dp = ctypes.c_void_p()
-    _lib.check(_lib.lib().mgvs_forward_diag(ctypes.byref(prob), ctypes.byref(dp)), "mgvs_forward_diag")
-    off = dp.value - ws.data_ptr()
-    a, b, c = ws[off:off + 24].view(torch.int64).cpu().tolist()
-    return a, b, float(torch.tensor([c], dtype=torch.int64).view(torch.float32)[0])
 
 
 class _ViewSynthesisLoss(torch.autograd.Function):
@@ -228,9 +206,6 @@ class _ViewSynthesisLoss(torch.autograd.Function):
                     world = allreduce_sums(sums, cfg.process_group)    # same exchange through NCCL
                     _lib.check(L.mgvs_finalize(ctypes.byref(prob), sums.data_ptr(), losses.data_ptr(), stream), "mgvs_finalize")
                 launch_counter.n += FIN_LAUNCHES
-        if cfg.collect_diag:
-            global last_forward_diag
-            last_forward_diag = forward_diag(prob, ws)
         ctx.cfg = cfg
         ctx.n = n
         ctx.has_mask = mask is not None

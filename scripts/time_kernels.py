@@ -9,7 +9,7 @@ from mgnet_b200.ops import LossConfig, _fill_problem
 from mgnet_b200.synthetic import make_inputs
 W = {"c1": (1, 192, 640, 3), "c2": (16, 192, 640, 3), "c3": (8, 512, 1024, 4), "c4": (8, 1024, 2048, 3), "c2n1": (16, 192, 640, 1)}
 names = sys.argv[1:] or ["c2", "c3"]
-dev = torch.device("cuda:0"); L = _lib.lib(); cfg = LossConfig(forward_mode=os.environ.get("MGVS_FORWARD_MODE", "exact"))
+dev = torch.device("cuda:0"); L = _lib.lib(); cfg = LossConfig()
 res = []
 for name in names:
     B, H, Wd, n = W[name]
@@ -32,7 +32,5 @@ for name in names:
         _lib.check(L.mgvs_backward(ctypes.byref(prob), sel.data_ptr(), sums.data_ptr(), g.data_ptr(), arr, gp.data_ptr(), st)); c.record(); torch.cuda.synchronize()
         if it >= 3: tf.append(a.elapsed_time(b)); tb.append(b.elapsed_time(c))
     f, bb = statistics.median(tf), statistics.median(tb)
-    from mgnet_b200.ops import forward_diag
-    diag = forward_diag(prob, ws)
-    res.append("%s: fwd %.3f bwd %.3f ms -> %.3f Gpx/s (loss %.8f, rechecked %.4f%% changed %d max-ratio %.3f)" % (name, f, bb, B * H * Wd / ((f + bb) * 1e-3) / 1e9, losses[0].item(), 100.0 * diag[0] / (n * B * H * Wd), diag[1], diag[2]))
+    res.append("%s: fwd %.3f bwd %.3f ms -> %.3f Gpx/s (loss %.8f)" % (name, f, bb, B * H * Wd / ((f + bb) * 1e-3) / 1e9, losses[0].item()))
 print(os.environ.get("MGVS_LIB_PATH", "default"), os.environ.get("MGVS_BACKWARD", "stash"), " | ".join(res))

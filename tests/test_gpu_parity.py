@@ -33,13 +33,11 @@ def _to_dev(pred, tgt, dev, grad=True):
 BACKWARDS = ("stash", "recompute")   # both backward kernels must meet the same bars
 
 
-def _run_cuda(pred, tgt, hp, dev, g=(1.0, 1.0), backward="stash", forward_mode="exact", diag=False):
-    from mgnet_b200 import MultiViewPhotometricLoss, ops
-    mod = MultiViewPhotometricLoss(backward=backward, forward_mode=forward_mode, **hp)
-    mod.collect_diag = diag
+def _run_cuda(pred, tgt, hp, dev, g=(1.0, 1.0), backward="stash"):
+    from mgnet_b200 import MultiViewPhotometricLoss
+    mod = MultiViewPhotometricLoss(backward=backward, **hp)
     p, t = _to_dev(pred, tgt, dev)
     out = mod(p, t)
-    fwd_diag = ops.last_forward_diag if diag else None
     (g[0] * out["loss_photometric"] + g[1] * out["loss_smoothness"]).backward()
     torch.cuda.synchronize()
     return {
@@ -48,7 +46,6 @@ def _run_cuda(pred, tgt, hp, dev, g=(1.0, 1.0), backward="stash", forward_mode="
         "sel": mod.last_selection.cpu().numpy() if mod.last_selection is not None else None,
         "grad_depth": [d.grad.cpu().numpy() for d in p["depth"]],
         "grad_poses": p["poses"].grad.cpu().numpy(),
-        "diag": fwd_diag,
     }
 
 
