@@ -346,11 +346,14 @@ def main():
     dominant = "bwd" if bwd_ms >= fwd_ms else "fwd"
     dom_ms = bwd_ms if dominant == "bwd" else fwd_ms
     achieved = px_gpu * bpp[dominant] / (dom_ms * 1e-3) / 1e9
+    # DRAM bytes of the dominant kernel per launch: ncu (--set full, dram__bytes_read + dram__bytes_write) cannot run inside a timed
+    # bench, so the per-pixel figure of the last capture of this image size / path (profiles/traffic.json, which names the report)
+    # is scaled to the pixels of this launch; null when no capture of this shape exists
     traffic = None
     try:
         with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
-            traffic = json.load(f).get(args.workload, {}).get(
-                dominant + ("_stash" if args.backward == "stash" else "") + "_kernel_dram_bytes_per_launch")
+            per_px = json.load(f).get("per_pixel", {}).get("%dx%d_n%d" % (H, W, n), {}).get(dominant + ("_stash" if args.backward == "stash" else ""))
+        traffic = int(per_px * px_gpu) if per_px else None
     except Exception:
         pass
     roofline = {"bound": "hbm", "kernel": dominant + "_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",

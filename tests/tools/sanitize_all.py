@@ -41,4 +41,23 @@ for (H, W, pan) in ((48, 160, True), (37, 75, True), (40, 64, False)):
                                   0 if pan else -1, [10000] if pan else [])
     torch.cuda.synchronize()
     print("dgc", H, W, pan, float(scale[0]), int(cnt[0]))
+# round 2: pose-matrix input, bit-packed mask, PoseCNN tail, stand-alone geometry kernels with two cameras
+from mgnet_b200.geometry import Camera, Pose, view_synthesis
+from mgnet_b200.pose_tail import pose_tail
+from mgnet_b200.synthetic import pack_mask
+pred, tgt = make_inputs(2, 37, 75, 2, seed=6, pose_scale=0.05)
+mats = torch.stack([Pose.from_vec(pred["poses"][:, s], "euler").mat for s in range(2)], 1)
+print("pose matrices", run(base, {"depth": pred["depth"], "poses": mats}, tgt))
+print("packed mask", run(base, pred, dict(tgt, reprojection_mask=pack_mask(tgt["reprojection_mask"]))))
+feat = torch.randn(2, 12, 5, 9, device=dev, requires_grad=True)
+pose_tail(feat).sum().backward()
+K = tgt["camera_matrix"][:, :3, :3].contiguous().to(dev)
+cam, ref_cam = Camera(K.clone()).to(dev), Camera(K.clone(), Tcw=Pose(mats[:, 0].to(dev))).scaled(0.9, 1.05)
+depth = (1.0 / pred["depth"][0].clamp(min=1e-6)).to(dev)
+for pad in ("zeros", "border", "reflection"):
+    view_synthesis(tgt["image_prev_orig"].to(dev), depth, ref_cam, cam, padding_mode=pad, return_coords=True)
+X = cam.reconstruct(depth, frame="c")
+ref_cam.project(X, frame="w")
+torch.cuda.synchronize()
+print("geometry ops ok")
 print("SANITIZE_DONE")
