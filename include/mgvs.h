@@ -25,7 +25,7 @@ extern "C" {
 
 #define MGVS_ABI_VERSION 7   /* v2 image_dtype, v3 stash, v4 inv_height/inv_width, v5 padding modes, ssim_weight == 0, DGC, uncertainty, peer exchange,
                                 v6 pose_mats, camera_lift of mgvs_view_synthesis_ex, exchange status word,
-                                v7 mgvs_unpack_mask (bit-packed reprojection mask), mgvs_pose_tail_* */
+                                v7 mgvs_unpack_mask (bit-packed reprojection mask), mgvs_pose_tail_*, mgvs_workspace_bytes_ex2 (upsample pre-pass) */
 #define MGVS_MAX_SCALES 8   /* n: number of inverse-depth maps (reference: 3, mg_net.py:760-764) */
 #define MGVS_NUM_SOURCES 2  /* S: prev, next -- hard-coded in the reference (loss.py:116) */
 
@@ -85,11 +85,12 @@ typedef struct MgvsProblem {
     int inv_width[MGVS_MAX_SCALES];  /* (the reference's contract).  Otherwise inv_depth[i] is the depth head's low-resolution
                                    map [B,1,inv_height[i],inv_width[i]] BEFORE its F.interpolate(scale_factor=stride,
                                    mode="bilinear", align_corners=True) (mg_net.py:803-806), with H = h*s and W = w*s for an
-                                   integer s: the kernels apply that upsample themselves, bit-identically to ATen's CPU
-                                   kernel, and mgvs_backward returns grad_inv[i] at the LOW resolution (the adjoint of the
-                                   upsample is applied in fixed order: deterministic, unlike ATen's atomics on CUDA).  All
-                                   maps must be low resolution or none; needs the stash (mgvs_stash_bytes_ex(..., 1)),
-                                   W % 4 == 0 and 16-byte aligned image tensors. */
+                                   integer s: mgvs_forward applies that upsample itself (an HBM-bound pre-pass into the workspace,
+                                   bit-identical to ATen's CPU kernel; both big kernels then read the full-resolution maps by TMA) and
+                                   mgvs_backward returns grad_inv[i] at the LOW resolution (the adjoint of the upsample is applied in
+                                   fixed order: deterministic, unlike ATen's atomics on CUDA).  All maps must be low resolution or
+                                   none; needs the stash (mgvs_stash_bytes_ex(..., 1)), a workspace sized by
+                                   mgvs_workspace_bytes_ex2(..., 1) and W % 4 == 0. */
     const float *pose_mats;     /* optional [B,S,3,4] row-major (R|t): rows 0..2 of the 4x4 the reference builds with
                                    Pose.from_vec -> pose_vec2mat (pose.py:41-47, pose_utils.py:41-51).  Non-NULL replaces the in-kernel
                                    Euler evaluation of `poses`: a caller that forms R with torch gets the reference's own rotation bits
@@ -105,6 +106,8 @@ const char *mgvs_last_error(void);
 size_t mgvs_workspace_bytes(int B, int H, int W, int n);
 /* Same for a given image_dtype (uint8 ingestion keeps float copies of the three images in the workspace). */
 size_t mgvs_workspace_bytes_ex(int B, int H, int W, int n, int image_dtype);
+/* Same with fused_upsample != 0: room for the n full-resolution inverse-depth maps the upsample pre-pass of mgvs_forward writes. */
+size_t mgvs_workspace_bytes_ex2(int B, int H, int W, int n, int image_dtype, int fused_upsample);
 
 /* Size of the optional coefficient stash (MgvsProblem.stash). */
 size_t mgvs_stash_bytes(int B, int H, int W, int n);

@@ -141,6 +141,8 @@ def lib():
     L.mgvs_workspace_bytes.argtypes = [ci, ci, ci, ci]
     L.mgvs_workspace_bytes_ex.restype = ctypes.c_size_t
     L.mgvs_workspace_bytes_ex.argtypes = [ci, ci, ci, ci, ci]
+    L.mgvs_workspace_bytes_ex2.restype = ctypes.c_size_t
+    L.mgvs_workspace_bytes_ex2.argtypes = [ci, ci, ci, ci, ci, ci]
     L.mgvs_stash_bytes.restype = ctypes.c_size_t
     L.mgvs_stash_bytes.argtypes = [ci, ci, ci, ci]
     L.mgvs_stash_bytes_ex.restype = ctypes.c_size_t
@@ -191,7 +193,7 @@ def lib():
 
 
 EXPORTED_SYMBOLS = (
-    "mgvs_abi_version", "mgvs_last_error", "mgvs_num_sums", "mgvs_workspace_bytes", "mgvs_workspace_bytes_ex", "mgvs_stash_bytes", "mgvs_stash_bytes_ex", "mgvs_forward", "mgvs_forward_losses",
+    "mgvs_abi_version", "mgvs_last_error", "mgvs_num_sums", "mgvs_workspace_bytes", "mgvs_workspace_bytes_ex", "mgvs_workspace_bytes_ex2", "mgvs_stash_bytes", "mgvs_stash_bytes_ex", "mgvs_forward", "mgvs_forward_losses",
     "mgvs_finalize", "mgvs_backward", "mgvs_view_synthesis", "mgvs_view_synthesis_ex", "mgvs_reconstruct", "mgvs_project", "mgvs_test_div", "mgvs_unpack_mask", "mgvs_pose_tail_forward", "mgvs_pose_tail_backward",
     "mgvs_dgc_workspace_bytes", "mgvs_dgc_rescale", "mgvs_dgc_heights",
     "mgvs_uncertainty_forward", "mgvs_uncertainty_backward",

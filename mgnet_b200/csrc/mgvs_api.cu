@@ -107,12 +107,13 @@ static bool make_stash_map(TmaDesc* out, const void* base, int planes, int H, in
 // stash = coefficient texels [n][B][3][H][4][Wg] float4, then the two masked edge-aware weight planes [2B][H][4*Wg] floats
 static size_t stash_texel_bytes(int B, int H, int W, int n) { return align256((size_t)n * B * 3 * H * 4 * ((W + 3) / 4) * sizeof(float4)); }
 static size_t stash_weight_bytes(int B, int H, int W) { return align256((size_t)2 * B * H * 4 * ((W + 3) / 4) * sizeof(float)); }
-// fused upsample: + the n full-resolution depth-gradient maps the upsample adjoint reads
+// fused upsample: + the n full-resolution depth-gradient maps the upsample adjoint reads and one [B][H][W/2] scratch for the
+// separable adjoint (any stride >= 2)
+static size_t stash_map_stride(int B, int H, int W) { return align256((size_t)B * H * W * sizeof(float)); }
 static size_t stash_bytes(int B, int H, int W, int n, bool lowres = false)
 {
-    // + one [B][H][W/2] scratch for the separable adjoint (any stride >= 2)
     return stash_texel_bytes(B, H, W, n) + stash_weight_bytes(B, H, W) +
-           (lowres ? (size_t)n * align256((size_t)B * H * W * sizeof(float)) + align256((size_t)B * H * ((W + 1) / 2) * sizeof(float)) : 0);
+           (lowres ? (size_t)n * stash_map_stride(B, H, W) + align256((size_t)B * H * ((W + 1) / 2) * sizeof(float)) : 0);
 }
 static int lowres_mode(const MgvsProblem* p)   // 0 = full resolution, 1 = all maps low resolution, -1 = invalid
 {
@@ -142,10 +143,10 @@ static bool tma_eligible(const MgvsProblem* p, const float* tgt, const float* sr
 // ---------------------------------------------------------------------------------------------
 // workspace layout (all offsets 256-byte aligned)
 struct Layout {
-    size_t cams, partials, imgsums, counter, pose_partials, packed[S], planar[1 + S], total;
+    size_t cams, partials, imgsums, counter, pose_partials, packed[S], planar[1 + S], invfull, total;
     int tiles_x, tiles_y, tiles;
 };
-static Layout make_layout(int B, int H, int W, int n, int image_dtype = 0)
+static Layout make_layout(int B, int H, int W, int n, int image_dtype = 0, bool lowres = false)
 {
     Layout L;
     L.tiles_x = (W + TW - 1) / TW;
@@ -164,6 +165,10 @@ static Layout make_layout(int B, int H, int W, int n, int image_dtype = 0)
         L.planar[k] = off;
         if (image_dtype == MGVS_IMAGE_U8) off = align256(off + sizeof(float) * (size_t)B * 3 * H * W);
     }
+    // fused upsample: the n full-resolution inverse-depth maps the upsample pre-pass writes and both big kernels read (last, so that
+    // every other offset is the same with and without it)
+    L.invfull = off;
+    if (lowres) off += (size_t)n * stash_map_stride(B, H, W);
     L.total = off;
     return L;
 }
@@ -582,6 +587,26 @@ __global__ void project_kernel(int B, int H, int W, const float* __restrict__ X,
 // real = r*i in [p-1, p+1), and 1/r = s + (s-1)/(n_in-1) lies in [s, 2s): i in [(p-1)*s - 1, (p+1)*s + 2s]; exact
 // membership is decided per element.
 // G lanes (a power of two <= 32, about half the stride) share one output and combine with a fixed-order xor butterfly.
+// ---- fused head-side upsample, forward half: the head's F.interpolate(bilinear, align_corners=True) as an HBM-bound pre-pass ----
+// (round 1 evaluated upsample_at() inside the two big kernels, once per tile and scale; those kernels are issue-bound and paid
+// ~7 % each for it, while this pass moves 4 B/px/scale at HBM speed: 2.9 ms -> 0.3 ms per step at B=64 1024x2048.)  Same
+// arithmetic, same bits as ATen's CPU kernel (mgvs_device.cuh upsample_at).  4 consecutive outputs per thread, 128-bit stores.
+__global__ void __launch_bounds__(256) upsample_kernel(int B, int H, int W, int h, int w, float ry, float rx, const float* __restrict__ low,
+                                                       float* __restrict__ full)
+{
+    const int W4 = W >> 2;
+    const long long total = (long long)B * H * W4;
+    for (long long idx = (long long)blockIdx.x * 256 + threadIdx.x; idx < total; idx += (long long)gridDim.x * 256) {
+        const int g = (int)(idx % W4);
+        const long long r = idx / W4;
+        const int v = (int)(r % H), b = (int)(r / H);
+        const LowRes lr = {low + (size_t)b * h * w, h, w, ry, rx};
+        float4 o;
+        o.x = upsample_at(lr, v, 4 * g); o.y = upsample_at(lr, v, 4 * g + 1); o.z = upsample_at(lr, v, 4 * g + 2); o.w = upsample_at(lr, v, 4 * g + 3);
+        *reinterpret_cast<float4*>(full + ((size_t)b * H + v) * W + 4 * g) = o;
+    }
+}
+
 template <int G>
 __global__ void __launch_bounds__(256) upsample_adjoint_h_kernel(int B, int H, int W, int w, float rx, const float* __restrict__ gfull,
                                                                  float* __restrict__ T)
@@ -657,9 +682,10 @@ static int check_problem(const MgvsProblem* p)
     if (!(p->ssim_weight > 0.f) && lowres_mode(p) != 0) return fail(MGVS_EUNSUPPORTED, "fused upsample with ssim_loss_weight == 0 (it needs the coefficient stash, which the L1-only branch does not have)");
     if (!p->workspace || ((uintptr_t)p->workspace & 255)) return fail(MGVS_EINVAL, "workspace null or not 256-byte aligned");
     if (p->image_dtype != MGVS_IMAGE_F32 && p->image_dtype != MGVS_IMAGE_U8) return fail(MGVS_EINVAL, "image_dtype must be MGVS_IMAGE_F32 or MGVS_IMAGE_U8");
-    if (p->workspace_bytes < make_layout(p->B, p->H, p->W, p->n, p->image_dtype).total) return fail(MGVS_EWORKSPACE, "workspace too small");
     const int lowres = lowres_mode(p);
     if (lowres < 0) return fail(MGVS_EINVAL, "inv_height/inv_width: all maps must be full resolution (0) or all low resolution with H = h*s, W = w*s");
+    if (p->workspace_bytes < make_layout(p->B, p->H, p->W, p->n, p->image_dtype, lowres != 0).total)
+        return fail(MGVS_EWORKSPACE, lowres ? "workspace too small (fused upsample: size it with mgvs_workspace_bytes_ex2(..., 1))" : "workspace too small");
     if (lowres && (p->W % 4 != 0)) return fail(MGVS_EUNSUPPORTED, "fused upsample needs W % 4 == 0");
     if (p->stash) {
         if ((uintptr_t)p->stash & 255) return fail(MGVS_EINVAL, "stash not 256-byte aligned");
@@ -883,6 +909,27 @@ __global__ void __launch_bounds__(256) unpack_mask_kernel(long long rows, int W,
     }
 }
 
+// Fused head-side upsample: writes the full-resolution maps F.interpolate(low, scale_factor=s, bilinear, align_corners=True)
+// into `dst` ([n] maps of stash_map_stride bytes) and rewrites the problem to point at them.  Called by the forward; the backward only
+// redirects (the maps are still there: the workspace must stay untouched between the two calls, include/mgvs.h).
+static void upsample_prepass(MgvsProblem* p, char* dst, cudaStream_t st, bool launch = true)
+{
+    const size_t stride = stash_map_stride(p->B, p->H, p->W);
+    for (int i = 0; i < p->n; i++) {
+        float* full = (float*)(dst + (size_t)i * stride);
+        if (launch) {
+            const int h = p->inv_height[i], w = p->inv_width[i];
+            const float ry = p->H > 1 ? (float)((double)(h - 1) / (double)(p->H - 1)) : 0.f;   // ATen: (in-1)/(out-1) in fp32
+            const float rx = p->W > 1 ? (float)((double)(w - 1) / (double)(p->W - 1)) : 0.f;
+            const long long total = (long long)p->B * p->H * (p->W >> 2);
+            const int blocks = (int)((total + 255) / 256 < 148 * 16 ? (total + 255) / 256 : 148 * 16);
+            upsample_kernel<<<blocks, 256, 0, st>>>(p->B, p->H, p->W, h, w, ry, rx, p->inv_depth[i], full);
+        }
+        p->inv_depth[i] = full;
+        p->inv_height[i] = 0; p->inv_width[i] = 0;
+    }
+}
+
 // ---- PoseCNN tail (reference layers.py:164-166): out[b, c] = 0.01 * mean_h(mean_w(x[b, c, h, w])) -----------------------------
 // One CTA per (b, c) map.  Rows are summed in fp64 in a fixed order (thread t takes rows t, t+128, ...; left to right inside a row),
 // the row means are folded by a fixed shuffle / shared-memory tree: deterministic, and within 1 ulp of the exactly rounded result
@@ -922,6 +969,12 @@ size_t mgvs_workspace_bytes_ex(int B, int H, int W, int n, int image_dtype)
     return make_layout(B, H, W, n, image_dtype).total;
 }
 size_t mgvs_workspace_bytes(int B, int H, int W, int n) { return mgvs_workspace_bytes_ex(B, H, W, n, MGVS_IMAGE_F32); }
+size_t mgvs_workspace_bytes_ex2(int B, int H, int W, int n, int image_dtype, int fused_upsample)
+{
+    if (B < 1 || H < 1 || W < 1 || n < 1 || n > MGVS_MAX_SCALES) return 0;
+    if (image_dtype != MGVS_IMAGE_F32 && image_dtype != MGVS_IMAGE_U8) return 0;
+    return make_layout(B, H, W, n, image_dtype, fused_upsample != 0).total;
+}
 size_t mgvs_stash_bytes_ex(int B, int H, int W, int n, int fused_upsample)
 {
     if (B < 1 || H < 1 || W < 1 || n < 1 || n > MGVS_MAX_SCALES) return 0;
@@ -942,6 +995,7 @@ int mgvs_forward_losses(const MgvsProblem* p_in, unsigned char* sel, double* sum
     cudaStream_t st = (cudaStream_t)cuda_stream;
     Layout L = make_layout(p->B, p->H, p->W, p->n, p->image_dtype);
     char* ws = (char*)p->workspace;
+    if (lowres_mode(p)) upsample_prepass(&pl, ws + L.invfull, st);     // from here on pl describes full-resolution maps in the workspace
     Cam* cams = (Cam*)(ws + L.cams);
     // float views of the three images: the caller's tensors, or the workspace copies written by pack_u8_kernel
     const bool u8 = p->image_dtype == MGVS_IMAGE_U8;
@@ -972,20 +1026,12 @@ int mgvs_forward_losses(const MgvsProblem* p_in, unsigned char* sel, double* sum
     fp.alpha = p->ssim_weight; fp.oma = p->one_minus_ssim_weight;
     fp.tiles_x = L.tiles_x; fp.tiles_y = L.tiles_y;
     FwdMaps maps;
-    const int lowres = lowres_mode(p);
     bool use_tma = tma_eligible(p, tgt_f, src_f[0], src_f[1]);
     if (use_tma) {
         use_tma = make_map(&maps.tgt, tgt_f, 3 * p->B, p->H, p->W, FWD_ROWS, 3) &&
                   make_map(&maps.src[0], src_f[0], 3 * p->B, p->H, p->W, FWD_ROWS, 3) &&
                   make_map(&maps.src[1], src_f[1], 3 * p->B, p->H, p->W, FWD_ROWS, 3);
-        for (int i = 0; i < p->n && use_tma && !lowres; i++) use_tma = make_map(&maps.inv[i], p->inv_depth[i], p->B, p->H, p->W, FWD_ROWS, 1);
-    }
-    if (lowres && !use_tma) return fail(MGVS_EUNSUPPORTED, "fused upsample needs 16-byte aligned image tensors (TMA path)");
-    fp.lowres = lowres;
-    for (int i = 0; i < p->n && lowres; i++) {
-        fp.inv_h[i] = p->inv_height[i]; fp.inv_w[i] = p->inv_width[i];
-        fp.inv_ry[i] = p->H > 1 ? (float)((double)(p->inv_height[i] - 1) / (double)(p->H - 1)) : 0.f;   // ATen: (in-1)/(out-1) in fp32
-        fp.inv_rx[i] = p->W > 1 ? (float)((double)(p->inv_width[i] - 1) / (double)(p->W - 1)) : 0.f;
+        for (int i = 0; i < p->n && use_tma; i++) use_tma = make_map(&maps.inv[i], p->inv_depth[i], p->B, p->H, p->W, FWD_ROWS, 1);
     }
     fp.early_wait = u8 ? 1 : 0;
     if (!use_tma) memset(&maps, 0, sizeof(maps));
@@ -1047,22 +1093,19 @@ int mgvs_backward(const MgvsProblem* p_in, const unsigned char* sel, const doubl
         memset(&sp, 0, sizeof(sp));
         sp.B = p->B; sp.H = p->H; sp.W = p->W; sp.n = p->n; sp.automask = p->automask; sp.pad = p->padding_mode;
         sp.tgt = tgt_f;
+        // fused upsample: the kernel reads the full-resolution maps the forward's pre-pass left in the workspace and writes
+        // full-resolution gradients into the stash tail; the adjoint kernels fold those down into the caller's low-resolution grad_inv[i]
         const int lowres = lowres_mode(p);
-        // fused upsample: the kernel writes full-resolution gradients into the stash tail, the adjoint kernel folds them
-        // down into the caller's low-resolution grad_inv[i]
+        int low_h[MGVS_MAX_SCALES], low_w[MGVS_MAX_SCALES];
+        for (int i = 0; i < p->n; i++) { low_h[i] = p->inv_height[i]; low_w[i] = p->inv_width[i]; }
+        if (lowres) upsample_prepass(&pl, ws + L.invfull, st, /*launch=*/false);
         char* gfull = (char*)p->stash + stash_texel_bytes(p->B, p->H, p->W, p->n) + stash_weight_bytes(p->B, p->H, p->W);
-        const size_t gfull_stride = align256((size_t)p->B * p->H * p->W * sizeof(float));
+        const size_t gfull_stride = stash_map_stride(p->B, p->H, p->W);
         float* adjT = (float*)(gfull + (size_t)p->n * gfull_stride);
-        sp.lowres = lowres;
         for (int i = 0; i < p->n; i++) {
             sp.inv[i] = p->inv_depth[i];
             if (!grad_inv[i]) return fail(MGVS_EINVAL, "null grad_inv pointer");
             sp.grad_inv[i] = lowres ? (float*)(gfull + (size_t)i * gfull_stride) : grad_inv[i];
-            if (lowres) {
-                sp.inv_h[i] = p->inv_height[i]; sp.inv_w[i] = p->inv_width[i];
-                sp.inv_ry[i] = p->H > 1 ? (float)((double)(p->inv_height[i] - 1) / (double)(p->H - 1)) : 0.f;
-                sp.inv_rx[i] = p->W > 1 ? (float)((double)(p->inv_width[i] - 1) / (double)(p->W - 1)) : 0.f;
-            }
         }
         sp.mask = p->mask; sp.cams = (const Cam*)(ws + L.cams); sp.sel = sel; sp.sums = sums;
         sp.psrc[0] = (const float4*)(ws + L.packed[0]); sp.psrc[1] = (const float4*)(ws + L.packed[1]);
@@ -1080,7 +1123,7 @@ int mgvs_backward(const MgvsProblem* p_in, const unsigned char* sel, const doubl
         bool tma_img = tma_eligible(p, tgt_f, src_f[0], src_f[1]);
         if (tma_img) {
             tma_img = make_map(&smaps.tgt, tgt_f, 3 * p->B, p->H, p->W, BS_ROWS, 3);
-            for (int i = 0; i < p->n && tma_img && !lowres; i++) tma_img = make_map(&smaps.inv[i], p->inv_depth[i], p->B, p->H, p->W, BS_ROWS, 1);
+            for (int i = 0; i < p->n && tma_img; i++) tma_img = make_map(&smaps.inv[i], p->inv_depth[i], p->B, p->H, p->W, BS_ROWS, 1);
         }
         void (*kern)(BwdSParams, BwdSMaps) = p->padding_mode == 0 ? (tma_img ? bwd_stash_kernel<true> : bwd_stash_kernel<false>)
                                                                   : (tma_img ? bwd_stash_kernel<true, true> : bwd_stash_kernel<false, true>);
@@ -1088,8 +1131,10 @@ int mgvs_backward(const MgvsProblem* p_in, const unsigned char* sel, const doubl
         kern<<<L.tiles, NT, BS_SMEM_BYTES, st>>>(sp, smaps);
         pose_reduce_kernel<<<p->B * S, 128, 0, st>>>(L.tiles_x * L.tiles_y, sp.pose_partials, p->pose_mats ? nullptr : p->poses, grad_poses);
         for (int i = 0; i < p->n && lowres; i++) {
-            const int stride = p->H / sp.inv_h[i];
-            #define MGVS_ADJ(G) launch_upsample_adjoint<G>(p->B, p->H, p->W, sp.inv_h[i], sp.inv_w[i], sp.inv_ry[i], sp.inv_rx[i], sp.grad_inv[i], adjT, grad_inv[i], st)
+            const int stride = p->H / low_h[i];
+            const float ry = p->H > 1 ? (float)((double)(low_h[i] - 1) / (double)(p->H - 1)) : 0.f;   // ATen: (in-1)/(out-1) in fp32
+            const float rx = p->W > 1 ? (float)((double)(low_w[i] - 1) / (double)(p->W - 1)) : 0.f;
+            #define MGVS_ADJ(G) launch_upsample_adjoint<G>(p->B, p->H, p->W, low_h[i], low_w[i], ry, rx, sp.grad_inv[i], adjT, grad_inv[i], st)
             if (stride >= 64) MGVS_ADJ(32); else if (stride >= 32) MGVS_ADJ(16); else if (stride >= 16) MGVS_ADJ(8);
             else if (stride >= 8) MGVS_ADJ(4); else if (stride >= 4) MGVS_ADJ(2); else MGVS_ADJ(1);
             #undef MGVS_ADJ

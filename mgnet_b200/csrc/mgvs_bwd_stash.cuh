@@ -42,9 +42,6 @@ struct BwdSParams {
     float* pose_partials;         // [tiles][S*12]
     float alpha, oma, photo_w, smooth_w;
     int tiles_x, tiles_y;
-    int lowres;                   // fused head-side upsample: inv[i] are low-resolution maps (see FwdParams)
-    int inv_h[MAXN], inv_w[MAXN];
-    float inv_ry[MAXN], inv_rx[MAXN];
 };
 struct BwdSMaps {
     TmaDesc tgt, inv[MAXN], coef, wgt;     // wgt: the two masked edge-aware weight planes [2B][H][4*Wg] of the stash
@@ -203,17 +200,9 @@ __global__ void __launch_bounds__(NT, MIN_CTAS) bwd_stash_kernel(const __grid_co
             dst[idx] = (vv >= 0 && vv < H && uu >= 0 && uu < W) ? __ldg(img + (size_t)vv * W + uu) : 0.f;
         }
     };
-    // inverse-depth tiles: TMA from the full-resolution maps, or filled by hand (manual-loader build, or fused upsample
-    // of the head's low-resolution maps)
-    const bool inv_tma = USE_TMA && !p.lowres;
-    auto fill_inv = [&](int i, float* dst) {
-        if (p.lowres) {
-            LowRes lr = {p.inv[i] + (size_t)b * p.inv_h[i] * p.inv_w[i], p.inv_h[i], p.inv_w[i], p.inv_ry[i], p.inv_rx[i]};
-            fill_inv_tile_lowres<1, BS_ROWS>(dst, lr, x0, y0, H, W, tid);
-        } else {
-            load_plane_manual(p.inv[i] + (size_t)b * HW, dst);
-        }
-    };
+    // inverse-depth tiles: TMA from the full-resolution maps, or filled by hand (manual-loader build)
+    constexpr bool inv_tma = USE_TMA;
+    auto fill_inv = [&](int i, float* dst) { load_plane_manual(p.inv[i] + (size_t)b * HW, dst); };
     if (tid == 0) {
         tma::mbar_init(sBar + 0, 1); tma::mbar_init(sBar + 1, 1); tma::mbar_init(sBar + 2, 1); tma::mbar_init(sBar + 3, 1);
         tma::fence_barrier_init();

@@ -28,9 +28,6 @@ struct FwdParams {
     float4* stash;               // STASH kernels only: SSIM-adjoint coefficient texels for the stash backward (see below)
     int Wg;                      // ceil(W/4): column groups per stash row
     float* wgt;                  // STASH kernels only: masked edge-aware weight planes [2B][H][4*Wg] (pairs (q,q+1) and (q,q+W))
-    int lowres;                  // fused head-side upsample: inv[i] are low-resolution maps [B][inv_h[i]][inv_w[i]] (TMA kernels only)
-    int inv_h[MAXN], inv_w[MAXN];
-    float inv_ry[MAXN], inv_rx[MAXN];
     double* partials;            // [tiles][4n+3]
     float alpha, oma;
     int tiles_x, tiles_y;
@@ -177,10 +174,8 @@ __global__ void __launch_bounds__(NT, MIN_CTAS) fwd_kernel(const FwdParams p, co
             tma::load_3d(sY, &maps.tgt, x0 - XOFF, y0 - 1, 3 * b, sBar + 0);
             tma::load_3d(sX, &maps.src[0], x0 - XOFF, y0 - 1, 3 * b, sBar + 0);
             tma::load_3d(sX + FWD_TILE3_FLOATS, &maps.src[1], x0 - XOFF, y0 - 1, 3 * b, sBar + 0);
-            if (!p.lowres) {
-                tma::mbar_expect_tx(sBar + 1, FWD_CH * 4);
-                tma::load_3d(sInv, &maps.inv[0], x0 - XOFF, y0 - 1, b, sBar + 1);
-            }
+            tma::mbar_expect_tx(sBar + 1, FWD_CH * 4);
+            tma::load_3d(sInv, &maps.inv[0], x0 - XOFF, y0 - 1, b, sBar + 1);
         }
         __syncthreads();                 // barrier init visible
         tma::mbar_wait(sBar + 0, 0);
@@ -345,13 +340,7 @@ __global__ void __launch_bounds__(NT, MIN_CTAS) fwd_kernel(const FwdParams p, co
     for (int i = 0; i < p.n; i++) {
         const float* inv = p.inv[i] + (size_t)b * HW;
         const float* sI = sInv + (i & 1) * FWD_INV_FLOATS;
-        if (USE_TMA && p.lowres) {
-            // fused upsample: build this scale's full-resolution tile from the low-resolution map (ring slot i & 1: its
-            // last readers finished two barriers ago)
-            LowRes lr = {p.inv[i] + (size_t)b * p.inv_h[i] * p.inv_w[i], p.inv_h[i], p.inv_w[i], p.inv_ry[i], p.inv_rx[i]};
-            fill_inv_tile_lowres<1, FWD_ROWS>(sInv + (i & 1) * FWD_INV_FLOATS, lr, x0, y0, H, W, tid);
-            __syncthreads();
-        } else if (USE_TMA) {
+        if (USE_TMA) {
             // prefetch the next scale's inverse-depth tile into the other ring slot (its last readers
             // finished before the barrier that ended the previous scale), then wait for this scale's tile
             if (tid == 0 && i + 1 < p.n) {

@@ -23,7 +23,7 @@ class _Counter:
 
 
 launch_counter = _Counter()
-FWD_LAUNCHES = 3   # pack_sources_kernel (+camera table), fwd_kernel, reduce_kernel
+FWD_LAUNCHES = 3   # pack_sources_kernel (+camera table), fwd_kernel, reduce_kernel (+ one upsample_kernel per scale with fuse_upsample)
 FIN_LAUNCHES = 1   # finalize_kernel
 BWD_LAUNCHES = 2   # bwd_kernel, pose_reduce_kernel
 
@@ -44,9 +44,9 @@ class LossConfig:
                                       # full-batch gradient; only with process_group
     fuse_upsample: bool = False       # predictions["depth"][i] are the depth head's LOW-resolution maps
                                       # [B,1,H/s,W/s] (after sigmoid()/0.5, before its F.interpolate(scale_factor=s,
-                                      # mode="bilinear", align_corners=True), mg_net.py:803-806,823); the kernels upsample on
-                                      # the fly (bit-identical to ATen's CPU kernel) and return low-resolution gradients
-                                      # through a deterministic adjoint.  Needs backward="stash".
+                                      # mode="bilinear", align_corners=True), mg_net.py:803-806,823); the library upsamples them
+                                      # itself (an HBM-bound pre-pass, bit-identical to ATen's CPU kernel) and returns
+                                      # low-resolution gradients through a deterministic adjoint.  Needs backward="stash".
     backward: str = "stash"           # "stash": the forward also writes the SSIM-adjoint coefficient texels of the
                                       # selected source (48 B/px/scale) and the backward consumes them (fastest);
                                       # "recompute": nothing but the uint8 selection is carried over and the backward
@@ -180,7 +180,7 @@ class _ViewSynthesisLoss(torch.autograd.Function):
         # (ssim_loss_weight == 0, the raw-L1 branch, has no SSIM adjoint to stash: the library runs its recompute backward)
         want_stash = cfg.backward == "stash" and cfg.ssim_loss_weight > 0 and any(ctx.needs_input_grad[i] for i in (1,) + tuple(range(7, 7 + n)))
         with torch.cuda.device(dev):
-            ws = torch.empty(int(L.mgvs_workspace_bytes_ex(B, H, W, n, img_dtype)), dtype=torch.uint8, device=dev)
+            ws = torch.empty(int(L.mgvs_workspace_bytes_ex2(B, H, W, n, img_dtype, int(cfg.fuse_upsample))), dtype=torch.uint8, device=dev)
             stash = torch.empty(int(L.mgvs_stash_bytes_ex(B, H, W, n, int(cfg.fuse_upsample))), dtype=torch.uint8, device=dev) if want_stash else None
             sel = torch.empty((n, B, H, W), dtype=torch.uint8, device=dev)
             sums = torch.empty(3 * n + 3, dtype=torch.float64, device=dev)
@@ -193,10 +193,10 @@ class _ViewSynthesisLoss(torch.autograd.Function):
                 # single rank: the reduction's last block also writes the two losses (no finalize launch)
                 _lib.check(L.mgvs_forward_losses(ctypes.byref(prob), sel.data_ptr(), sums.data_ptr(), losses.data_ptr(), stream),
                            "mgvs_forward_losses")
-                launch_counter.n += FWD_LAUNCHES
+                launch_counter.n += FWD_LAUNCHES + (n if cfg.fuse_upsample else 0)
             else:
                 _lib.check(L.mgvs_forward(ctypes.byref(prob), sel.data_ptr(), sums.data_ptr(), stream), "mgvs_forward")
-                launch_counter.n += FWD_LAUNCHES
+                launch_counter.n += FWD_LAUNCHES + (n if cfg.fuse_upsample else 0)
                 if cfg.exchange is not None:
                     # the only inter-GPU exchange of the path, fused with the finalize: P2P pushes over NVLink in one kernel
                     world = cfg.exchange.world

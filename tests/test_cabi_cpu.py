@@ -35,6 +35,9 @@ def test_host_side_queries():
     assert ws > 0 and ws % 256 == 0
     assert L.mgvs_stash_bytes(16, 192, 640, 3) == 3 * 16 * 3 * 192 * 640 * 16 + 2 * 16 * 192 * 640 * 4   # 48 B per (pixel, scale) + 8 B per pixel
     assert L.mgvs_stash_bytes(1, 50, 70, 2) >= 2 * 1 * 3 * 50 * 4 * 18 * 16 + 2 * 50 * 72 * 4   # ragged W: ceil(70/4) column groups
+    # fused upsample keeps the n full-resolution inverse-depth maps of its pre-pass in the workspace (256-byte aligned maps)
+    assert L.mgvs_workspace_bytes_ex2(16, 192, 640, 3, 0, 0) == ws
+    assert L.mgvs_workspace_bytes_ex2(16, 192, 640, 3, 0, 1) == ws + 3 * 16 * 192 * 640 * 4
     assert L.mgvs_workspace_bytes(0, 192, 640, 3) == 0
     assert L.mgvs_workspace_bytes(1, 192, 640, 9) == 0
 
