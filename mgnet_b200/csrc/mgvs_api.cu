@@ -1047,8 +1047,10 @@ int mgvs_forward_losses(const MgvsProblem* p_in, unsigned char* sel, double* sum
         if (l1only)   // ssim_loss_weight == 0: raw 3-channel L1, 12-way min (loss.py:195-196); never with the stash
             kern = p->padding_mode == 0 ? (use_tma ? fwd_kernel<true, false, false, true> : fwd_kernel<false, false, false, true>)
                                         : (use_tma ? fwd_kernel<true, false, true, true> : fwd_kernel<false, false, true, true>);
-        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, FWD_SMEM_BYTES);
-        launch_pdl(kern, dim3(L.tiles), dim3(NT), FWD_SMEM_BYTES, st, fp, maps);
+        // (ablation 32: request enough shared memory that only ONE CTA fits an SM -- how the kernels scale with resident warps)
+        constexpr int fwd_smem = FWD_SMEM_BYTES + ((MGVS_ABL & 32) ? 40 * 1024 : 0);
+        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, fwd_smem);
+        launch_pdl(kern, dim3(L.tiles), dim3(NT), fwd_smem, st, fp, maps);
     }
     launch_pdl(reduce_kernel, dim3(p->B), dim3(256), 0, st, p->B, p->n, L.tiles_x * L.tiles_y, (long long)p->H * p->W,
                (const double*)fp.partials, (double*)(ws + L.imgsums), (unsigned int*)(ws + L.counter), sums,
@@ -1127,8 +1129,9 @@ int mgvs_backward(const MgvsProblem* p_in, const unsigned char* sel, const doubl
         }
         void (*kern)(BwdSParams, BwdSMaps) = p->padding_mode == 0 ? (tma_img ? bwd_stash_kernel<true> : bwd_stash_kernel<false>)
                                                                   : (tma_img ? bwd_stash_kernel<true, true> : bwd_stash_kernel<false, true>);
-        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, BS_SMEM_BYTES);
-        kern<<<L.tiles, NT, BS_SMEM_BYTES, st>>>(sp, smaps);
+        constexpr int bs_smem = BS_SMEM_BYTES + ((MGVS_ABL & 32) ? 40 * 1024 : 0);
+        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bs_smem);
+        kern<<<L.tiles, NT, bs_smem, st>>>(sp, smaps);
         pose_reduce_kernel<<<p->B * S, 128, 0, st>>>(L.tiles_x * L.tiles_y, sp.pose_partials, p->pose_mats ? nullptr : p->poses, grad_poses);
         for (int i = 0; i < p->n && lowres; i++) {
             const int stride = p->H / low_h[i];
