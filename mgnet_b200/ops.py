@@ -238,11 +238,15 @@ class _ViewSynthesisLoss(torch.autograd.Function):
         inv = list(saved[k:])
         dev = tgt.device
         with torch.cuda.device(dev):
-            g = torch.zeros(2, dtype=torch.float32, device=dev)
-            if g_photo is not None:
-                g[0] = g_photo
-            if g_smooth is not None:
-                g[1] = g_smooth
+            # the two upstream gradients as one [2] device vector: one launch when both are there (the usual case)
+            if g_photo is not None and g_smooth is not None:
+                g = torch.stack((g_photo.reshape(()).float(), g_smooth.reshape(()).float()))
+            else:
+                g = torch.zeros(2, dtype=torch.float32, device=dev)
+                if g_photo is not None:
+                    g[0] = g_photo
+                if g_smooth is not None:
+                    g[1] = g_smooth
             if ctx.grad_scale != 1.0:
                 g = g * ctx.grad_scale
             grads = [torch.empty_like(d) for d in inv]
