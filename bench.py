@@ -146,9 +146,32 @@ def cpu_reference_run(desc, B_sample, H, W, n, steps, warmup, seed=0):
         step()
     dt = (time.perf_counter() - t0) / max(steps, 1)
     px = B_sample * H * W
-    sample = "%d of the workload's images per step (B=%d, %dx%d, n=%d), %d steps after %d warm-up, torch %s, %d threads" % (
-        B_sample, B_sample, H, W, n, steps, warmup, torch.__version__, torch.get_num_threads())
+    sample = ("one step = fwd+bwd of %d of the workload's images (B=%d, %dx%d, n=%d) on all host cores -- the CPU arm's throughput does not depend on how many "
+              "such steps make up the batch (BASELINE.md section 4); %d steps after %d warm-up, torch %s, %d threads" % (
+                  B_sample, B_sample, H, W, n, steps, warmup, torch.__version__, torch.get_num_threads()))
     return px / dt / 1e9, dt * 1e3, {"cores": cores, "kind": "port", "sample": sample}
+
+
+def input_sets(B, H, W, n):
+    """Rotating input sets so that no step finds its inputs in L2 (returns count, bytes per set)."""
+    in_bytes = B * H * W * (36 + 4 * n + 1)
+    nsets = max(2, min(6, -(-3 * L2_BYTES // in_bytes))) if in_bytes < 2 * L2_BYTES else 2
+    return nsets, in_bytes
+
+
+def workload_config(desc, B, H, W, n, world, backward, peer_exchange, bpp):
+    """`config` of the JSON line -- the same dictionary for the B200 arm and for --impl reference (which times a bounded sample of
+    this workload on the host cores and says so in cpu_baseline.sample)."""
+    nsets, in_bytes = input_sets(B, H, W, n)
+    if world > 1:
+        how = "fused peer-memory exchange (NVLink P2P stores + flags, one kernel)" if peer_exchange else "one NCCL all-reduce"
+        par = "batch-sharded x%d, %s of %d doubles per step" % (world, how, 3 * n + 3)
+    else:
+        par = "single GPU"
+    return {"workload": desc, "B_per_gpu": B, "H": H, "W": W, "scales": n, "sources": 2, "mask": True,
+            "l2": "rotating %d input sets (%.0f MB) so inputs are never L2-resident" % (nsets, nsets * in_bytes / 1e6),
+            "parallelism": par, "bytes_per_pixel_fwd_bwd": bpp["fwd_bwd"], "backward": backward,
+            "stash_bytes_per_pixel": (96 * n if backward == "stash" else 0)}
 
 
 def cpu_sample_batch(B, H, W):
@@ -204,9 +227,7 @@ def main():
             "impl": "reference", "metric": "view-synth loss fwd+bwd Gpixel/s", "value": val, "unit": "Gpixel/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
             "higher_is_better": True, "scaling": "strong" if strong else "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": desc, "B_per_step": Bs, "H": H, "W": W, "scales": n, "sources": 2, "mask": True,
-                       "sample": "one step = fwd+bwd of %d image(s) of the workload's shape on all host cores (the CPU arm's throughput does "
-                                 "not depend on how many such steps make up the batch; BASELINE.md section 4)" % Bs},
+            "config": workload_config(desc, B, H, W, n, world, args.backward, args.exchange == "peer", bpp),
             "cpu_baseline": dict(info, value=val, unit="Gpixel/s"),
             "e2e": {"value": val, "unit": "Gpixel/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0,
@@ -259,8 +280,7 @@ def main():
     mod = MultiViewPhotometricLoss(process_group=group, exchange=exchange, ddp_grad_scale=False, backward=args.backward, **HP)
 
     # rotating input sets so that no step finds its inputs in L2 (inputs of one set are < L2 for c1/c2)
-    in_bytes = B * H * W * (36 + 4 * n + 1)
-    nsets = max(2, min(6, -(-3 * L2_BYTES // in_bytes))) if in_bytes < 2 * L2_BYTES else 2
+    nsets, in_bytes = input_sets(B, H, W, n)
     sets_host, sets_dev = [], []
     for k in range(nsets):
         pred, tgt = make_inputs(B, H, W, n, seed=100 + 10 * rank + k)
@@ -487,11 +507,7 @@ def main():
             "metric": "view-synth loss fwd+bwd Gpixel/s", "value": value, "unit": "Gpixel/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
             "scaling": "strong" if strong else "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": desc, "B_per_gpu": B, "H": H, "W": W, "scales": n, "sources": 2, "mask": True,
-                       "l2": "rotating %d input sets (%.0f MB) so inputs are never L2-resident" % (nsets, nsets * in_bytes / 1e6),
-                       "parallelism": ("batch-sharded x%d, %s of %d doubles per step" % (world, "one NCCL all-reduce" if exchange is None else "fused peer-memory exchange (NVLink P2P stores + flags, one kernel)", 3 * n + 3)) if world > 1 else "single GPU",
-                       "bytes_per_pixel_fwd_bwd": bpp["fwd_bwd"], "backward": args.backward,
-                       "stash_bytes_per_pixel": (96 * n if args.backward == "stash" else 0)},
+            "config": workload_config(desc, B, H, W, n, world, args.backward, exchange is not None, bpp),
             "roofline": roofline, "cpu_baseline": cpu_base, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
             "hbm_frac_fwd_bwd": value / world * bpp["fwd_bwd"] / peak,
         }
