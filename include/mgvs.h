@@ -193,6 +193,8 @@ int mgvs_project(int B, int H, int W, const float *points, const float *camera, 
 typedef struct MgvsPeerExchange {
     int rank, world;                    /* 1 <= world <= MGVS_MAX_RANKS */
     void *peer_base[MGVS_MAX_RANKS];    /* >= mgvs_exchange_bytes() each, 16-byte aligned; peer_base[rank] is the local one */
+    unsigned long long max_spins;       /* wait bound in 20 ns polls of the peers' flags; 0 = the default 2^31 (>= 40 s).  Tests use a small
+                                           value to exercise the timeout path. */
 } MgvsPeerExchange;
 size_t mgvs_exchange_bytes(void);
 /*   sums [3n+3] double, in: this rank's partial sums (mgvs_forward); out: the global sums (what mgvs_backward takes)

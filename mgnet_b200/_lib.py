@@ -80,7 +80,8 @@ MAX_RANKS = 16
 
 class MgvsPeerExchange(ctypes.Structure):
     """include/mgvs.h: MgvsPeerExchange (peer-memory exchange of the partial sums)."""
-    _fields_ = [("rank", ctypes.c_int), ("world", ctypes.c_int), ("peer_base", ctypes.c_void_p * MAX_RANKS)]
+    _fields_ = [("rank", ctypes.c_int), ("world", ctypes.c_int), ("peer_base", ctypes.c_void_p * MAX_RANKS),
+                ("max_spins", ctypes.c_ulonglong)]
 
 
 def _sources():

@@ -748,7 +748,7 @@ __device__ __forceinline__ double ld_relaxed_sys_f64(const double* p)
 }
 __device__ __forceinline__ void st_relaxed_sys_f64(double* p, double v) { asm volatile("st.relaxed.sys.global.f64 [%0], %1;" ::"l"(p), "d"(v) : "memory"); }
 
-__global__ void __launch_bounds__(256) exchange_finalize_kernel(int n, int rank, int world, PeerPtrs peers, double* __restrict__ sums,
+__global__ void __launch_bounds__(256) exchange_finalize_kernel(unsigned long long max_spins, int n, int rank, int world, PeerPtrs peers, double* __restrict__ sums,
                                                                 float photo_w, float smooth_w, float* __restrict__ losses)
 {
     __shared__ unsigned long long s_step;
@@ -782,7 +782,7 @@ __global__ void __launch_bounds__(256) exchange_finalize_kernel(int n, int rank,
         unsigned long long spins = 0;
         while (ld_acquire_sys(f) != step) {
             __nanosleep(20);
-            if (++spins > (1ull << 31)) { s_timeout = 1; break; }
+            if (++spins > max_spins) { s_timeout = 1; break; }
         }
     }
     __syncthreads();
@@ -1304,7 +1304,7 @@ int mgvs_exchange_finalize(const MgvsProblem* p, const MgvsPeerExchange* x, doub
         pp.base[r] = r < x->world ? (char*)x->peer_base[r] : nullptr;
         if (r < x->world && (!pp.base[r] || ((uintptr_t)pp.base[r] & 15))) return fail(MGVS_EINVAL, "peer_base null or not 16-byte aligned");
     }
-    exchange_finalize_kernel<<<1, 256, 0, (cudaStream_t)cuda_stream>>>(p->n, x->rank, x->world, pp, sums, p->photometric_weight, p->smoothing_weight, losses);
+    exchange_finalize_kernel<<<1, 256, 0, (cudaStream_t)cuda_stream>>>(x->max_spins ? x->max_spins : (1ull << 31), p->n, x->rank, x->world, pp, sums, p->photometric_weight, p->smoothing_weight, losses);
     return check_launch("mgvs_exchange_finalize");
 }
 
