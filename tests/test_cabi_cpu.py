@@ -80,3 +80,18 @@ def test_cpu_tensors_fail_loudly_no_fallback():
     pred, tgt = make_inputs(1, 32, 64, 1, seed=0)
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         MultiViewPhotometricLoss(0.85, 1.0, 1e-3, True, "min", "zeros")(pred, tgt)
+
+
+def test_pack_mask_layout_is_numpy_packbits():
+    """mgnet_b200.synthetic.pack_mask: row-wise numpy.packbits (MSB first, rows padded to bytes) -- the layout mgvs_unpack_mask expects."""
+    import numpy as np
+    import torch
+    from mgnet_b200.synthetic import pack_mask
+    g = torch.Generator().manual_seed(0)
+    for W in (8, 13, 64, 75):
+        m = torch.rand(2, 1, 5, W, generator=g) < 0.5
+        p = pack_mask(m)
+        assert p.dtype == torch.uint8 and tuple(p.shape) == (2, 1, 5, (W + 7) // 8)
+        back = np.unpackbits(p.numpy(), axis=-1)[..., :W].astype(bool)
+        assert np.array_equal(back, m.numpy())
+        assert int(p[0, 0, 0, 0]) >> 7 == int(m[0, 0, 0, 0])          # most significant bit = first pixel of the row
